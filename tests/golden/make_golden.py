@@ -1,0 +1,139 @@
+"""Generate tests/golden/<case>.npz from the REFERENCE ITSELF (oracle/_ref/_refC.so, the unmodified reference
+rasterizer compiled by oracle/build_ref.py) on a B200, and print a first oracle-vs-reference comparison.
+
+Run on the GPU box:   python tests/golden/make_golden.py            (writes gpurun_out/golden/*.npz)
+then copy the files into tests/golden/ and commit them.  The inputs are not stored: tests/golden/cases.py
+regenerates them from seeds.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import cases  # noqa: E402
+import refutil  # noqa: E402
+import gs_oracle  # noqa: E402
+
+GRAD_NAMES = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
+
+
+def run_reference(refC, name):
+    c, scene, cam, bg, dL, extra = cases.build_inputs(name)
+    W, H, P = c["W"], c["H"], c["P"]
+    args, out = refutil.ref_forward(refC, scene, cam, bg, extra)
+    R, color, radii, geomB, binB, imgB = out
+    torch.cuda.synchronize()
+    res = dict(num_rendered=np.int64(R), color=color.cpu().numpy(), radii=radii.cpu().numpy())
+    res.update(refutil.decode_geom(geomB, P))
+    res.update(refutil.decode_binning(binB, R))
+    res.update(refutil.decode_image(imgB, W, H))
+    res["mark_visible"] = refC.mark_visible(scene.means3D.cuda(), cam.world_view_transform.cuda(),
+                                            cam.full_proj_transform.cuda()).cpu().numpy()
+    if c["backward"]:
+        grads = refutil.ref_backward(refC, args, out, dL, c["lam"])
+        torch.cuda.synchronize()
+        for n, g in zip(GRAD_NAMES, grads):
+            res[n] = g.cpu().numpy()
+        # a second run shows the reference's own atomic-order noise
+        grads2 = refutil.ref_backward(refC, args, out, dL, c["lam"])
+        for n, g, g2 in zip(GRAD_NAMES, grads, grads2):
+            res["noise_" + n] = np.float32((g - g2).abs().max().item() if g.numel() else 0.0)
+    if c["packed"]:
+        flat, pbc, cs, cn = scene.packed_sh()
+        E = refutil.EMPTY
+        o2 = refC.rasterize_gaussians_variableSH_bands(
+            bg.cuda(), scene.means3D.cuda(), E, scene.opacity.cuda(), scene.scales.cuda(), scene.rotations.cuda(), 1.0, E,
+            cam.world_view_transform.cuda(), cam.full_proj_transform.cuda(), math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5),
+            H, W, flat.cuda(), pbc.cuda(), cs.cuda(), cn.cuda(), scene.degrees.cuda(), cam.camera_center.cuda(), False, False)
+        res["packed_color"] = o2[1].cpu().numpy()
+        res["packed_radii"] = o2[2].cpu().numpy()
+        res["packed_num_rendered"] = np.int64(o2[0])
+    return res
+
+
+def oracle_run(name):
+    c, scene, cam, bg, dL, extra = cases.build_inputs(name)
+    kw = dict(viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, campos=cam.camera_center,
+              W=c["W"], H=c["H"], tan_fovx=math.tan(cam.FoVx * 0.5), tan_fovy=math.tan(cam.FoVy * 0.5))
+    cov, col = extra.get("cov3D_precomp"), extra.get("colors_precomp")
+    fwd = gs_oracle.forward(scene.means3D, scene.opacity, None if cov is not None else scene.scales,
+                            None if cov is not None else scene.rotations, None if col is not None else scene.sh,
+                            scene.degrees, col, cov, bg=bg, **kw)
+    bwd = None
+    if c["backward"]:
+        bwd = gs_oracle.backward(fwd, dL, scene.means3D, None if cov is not None else scene.scales,
+                                 None if cov is not None else scene.rotations, None if col is not None else scene.sh,
+                                 scene.degrees, bg=bg, lambda_sh_sparsity=c["lam"], **kw)
+    return fwd, bwd
+
+
+def compare(name, ref, fwd, bwd, log=print):
+    """Mismatch report oracle vs reference. Returns dict of counts."""
+    vis = ref["radii"] > 0
+    rep = {}
+
+    def cnt(key, a, b, mask=None):
+        a, b = np.asarray(a), np.asarray(b)
+        if mask is not None:
+            a, b = a[mask], b[mask]
+        n = int((a != b).sum())
+        rep[key] = n
+        extra = ""
+        if n and a.dtype.kind == "f":
+            extra = " max|d|=%.3g" % float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+        log(f"  [{name}] {key:22s} mismatches {n:8d} / {a.size}{extra}")
+
+    cnt("radii", ref["radii"], fwd["radii"])
+    cnt("tiles_touched", ref["tiles_touched"], fwd["tiles_touched"])
+    cnt("depths", ref["depths"], fwd["depths"], vis)
+    cnt("means2D", ref["means2D"], fwd["means2D"], vis)
+    cnt("cov3D", ref["cov3D"], fwd["cov3D"], vis)
+    cnt("conic", ref["conic_opacity"][:, :3], fwd["conic_opacity"][:, :3], vis)
+    cnt("opacity", ref["conic_opacity"][:, 3], fwd["conic_opacity"][:, 3], vis)
+    cnt("rgb", ref["rgb"], fwd["rgb"], vis)
+    cnt("clamped", ref["clamped"], fwd["clamped"], vis)
+    log(f"  [{name}] num_rendered ref {int(ref['num_rendered'])} oracle {fwd['num_rendered']}")
+    if int(ref["num_rendered"]) == fwd["num_rendered"]:
+        cnt("keys", ref["keys"], fwd["keys"])
+        cnt("point_list", ref["point_list"], fwd["point_list"])
+        cnt("ranges", ref["ranges"], fwd["ranges"])
+        nb = ~fwd["borderline"]
+        cnt("n_contrib", ref["n_contrib"], fwd["n_contrib"])
+        cnt("n_contrib(nonborder)", ref["n_contrib"], fwd["n_contrib"], nb)
+        cnt("final_T", ref["final_T"], fwd["final_T"])
+        d = np.abs(ref["color"] - fwd["color"])
+        rep["color_max"] = float(d.max())
+        rep["color_max_nonborder"] = float(d[:, nb].max())
+        log(f"  [{name}] color max|d| {d.max():.3g}  (non-borderline {d[:, nb].max():.3g}; borderline px {int((~nb).sum())})")
+    if bwd is not None:
+        for n in GRAD_NAMES:
+            a, b = ref[n].astype(np.float64), bwd[n].astype(np.float64).reshape(ref[n].shape)
+            err = np.abs(a - b).max()
+            scale = np.abs(a).max()
+            rep["grad_" + n] = float(err / (scale + 1e-30))
+            log(f"  [{name}] {n:14s} max|d| {err:.3g}  max|ref| {scale:.3g}  ref-noise {float(ref.get('noise_' + n, 0)):.3g}")
+    return rep
+
+
+def main():
+    refC = refutil.load_ref()
+    assert refC is not None, "oracle/_ref/_refC.so missing (run oracle/build_ref.py where /root/reference exists)"
+    out_dir = os.path.join(ROOT, "gpurun_out", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name in cases.CASES:
+        ref = run_reference(refC, name)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **ref)
+        fwd, bwd = oracle_run(name)
+        compare(name, ref, fwd, bwd)
+    print("golden written to", out_dir, {f: os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir)})
+
+
+if __name__ == "__main__":
+    main()
