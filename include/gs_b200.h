@@ -1,0 +1,165 @@
+/*
+ * gs_b200.h — C ABI of the B200-native differentiable Gaussian-splat rasterizer.
+ *
+ * Drop-in boundary: this library replaces L1+L0 of the reference
+ * (graphdeco-inria/reduced-3dgs, submodules/diff-gaussian-rasterization):
+ *
+ *   gsb_forward        <-  CudaRasterizer::Rasterizer::forward          (cuda_rasterizer/rasterizer.h:33-58,
+ *                                                                        rasterizer_impl.cu:359-504) and
+ *                          CudaRasterizer::Rasterizer::inferenceForward (rasterizer.h:88-115,
+ *                                                                        rasterizer_impl.cu:206-355; set sh_packed)
+ *   gsb_backward       <-  CudaRasterizer::Rasterizer::backward         (rasterizer.h:60-86, rasterizer_impl.cu:508-630)
+ *   gsb_mark_visible   <-  CudaRasterizer::Rasterizer::markVisible      (rasterizer.h:26-31, rasterizer_impl.cu:149-161)
+ *   gsb_alloc_fn       <-  std::function<char*(size_t)> resize callbacks (rasterize_points.cu:33-41 resizeFunctional)
+ *
+ * The torch-facing functions the reference binds in ext.cpp:17-20 (rasterize_gaussians,
+ * rasterize_gaussians_backward, rasterize_gaussians_variableSH_bands, mark_visible; signatures in
+ * rasterize_points.h:18-93) are re-hosted in Python on top of these entry points
+ * (reduced-3dgs_b200/diff_gaussian_rasterization/_C.py) — see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only, no torch / C++ types.  All pointers are DEVICE pointers
+ * unless marked [host].  fp32 contiguous tensors with the reference's contracts:
+ * opacities are RAW logits, scales exp-activated, rotations normalised (r,x,y,z), SH is [P,M,3]
+ * coefficient-major, matrices are the transposed (row-vector convention) 4x4 the reference passes.
+ * A NULL pointer means "absent" exactly where the reference accepts an empty tensor.
+ * Every function returns 0 on success; on failure a negative GSB_E* code, with gsb_last_error()
+ * giving the message (the reference throws std::runtime_error / AT_ERROR instead).
+ * The stream argument is a cudaStream_t passed as void* (0 = legacy default stream).
+ */
+#ifndef GS_B200_H_INCLUDED
+#define GS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSB_API __attribute__((visibility("default")))
+#else
+#define GSB_API
+#endif
+
+#define GSB_OK 0
+#define GSB_EINVAL (-1)   /* bad argument (e.g. missing tensor, P < 0)                       */
+#define GSB_ECUDA (-2)    /* a CUDA runtime call or kernel failed; see gsb_last_error()      */
+#define GSB_ENOMEM (-3)   /* an allocation callback returned NULL                            */
+#define GSB_ERANGE (-4)   /* number of (Gaussian,tile) instances does not fit 31 bits        */
+
+#define GSB_NUM_CODEBOOKS 20
+#define GSB_CODEBOOK_SIZE 256
+
+/* Scratch allocator: must return a device pointer to at least `nbytes` bytes, 256-byte aligned, that stays
+ * valid until the paired backward has run (it is the "geomBuffer / binningBuffer / imgBuffer" the reference
+ * returns to Python).  Replaces resizeFunctional, rasterize_points.cu:33-41. */
+typedef char* (*gsb_alloc_fn)(void* user, size_t nbytes);
+
+/* Codebook-quantised attributes (reduced-3dgs PLY layout, scene/gaussian_model.py:239-311, 371-387).
+ * Fused de-quantisation == centers[ids] of gaussian_model.py:371-387 followed by exp (scaling),
+ * normalize (rotation) of gaussian_model.py:141-146; opacity stays a logit (sigmoid is in-kernel anyway). */
+typedef struct GsbQuant {
+	const uint8_t* ids_dc;       /* [P,3]     codebook 0                                               */
+	const uint8_t* ids_rest;     /* [P,15,3]  codebook 1+k for coefficient k (shared by R,G,B)          */
+	const uint8_t* ids_opacity;  /* [P]       codebook 16 (centres are logits)                          */
+	const uint8_t* ids_scaling;  /* [P,3]     codebook 17 (centres are log-scales)                      */
+	const uint8_t* ids_rot;      /* [P,4]     col 0 -> codebook 18 (real), cols 1-3 -> codebook 19      */
+	const float* centers;        /* [20,256]  fp32 centres (order: README.md:132-150)                   */
+} GsbQuant;
+
+typedef struct GsbScene {
+	int32_t P;                   /* number of Gaussians                                                 */
+	int32_t M;                   /* SH coefficients per Gaussian in the dense tensor (sh.size(1)); 0 = none */
+	const float* means3D;        /* [P,3]                                                               */
+	const float* opacities;      /* [P]   raw logits (NULL when quant != NULL)                          */
+	const float* scales;         /* [P,3] or NULL                                                       */
+	const float* rotations;      /* [P,4] or NULL                                                       */
+	const float* cov3D_precomp;  /* [P,6] or NULL (exactly one of scales+rotations / cov3D_precomp)     */
+	const float* shs;            /* dense [P,M,3], or packed per-degree groups when sh_packed, or NULL  */
+	const float* colors_precomp; /* [P,3] or NULL (exactly one of shs / colors_precomp / quant)         */
+	const int32_t* degrees;      /* [P]   active SH degree 0..3 per Gaussian (dense layout)             */
+	float scale_modifier;
+	int32_t sh_packed;           /* != 0: variable-SH inference layout, forward.cu:19-36 getSHOffset    */
+	int32_t band_count[4];       /* [host] perBandPrimitiveCount (Gaussians are ordered by degree)      */
+	const uint8_t* prune_mask;   /* [P] or NULL; 1 = pruned: behaves as culled (radii 0, no instances, zero grads) */
+	const GsbQuant* quant;       /* [host struct] or NULL; when set, opacities/scales/rotations/shs are ignored */
+} GsbScene;
+
+typedef struct GsbCamera {
+	int32_t width, height;
+	float tan_fovx, tan_fovy;
+	const float* viewmatrix;     /* [16] world_view_transform  (transposed)                              */
+	const float* projmatrix;     /* [16] full_proj_transform   (transposed)                              */
+	const float* campos;         /* [3]                                                                  */
+	const float* background;     /* [3]                                                                  */
+	int32_t prefiltered;         /* reference flag: a culled Gaussian is then an error (auxiliary.h:150-155) */
+} GsbCamera;
+
+/* Optional debug exports of forward intermediates in the REFERENCE's layouts (GeometryState,
+ * rasterizer_impl.h:21-42), used by the parity tests; every pointer may be NULL. */
+typedef struct GsbDebug {
+	float* depths;          /* [P]     */
+	float* means2D;         /* [P,2]   */
+	float* cov3D;           /* [P,6]   */
+	float* conic_opacity;   /* [P,4]   */
+	float* rgb;             /* [P,3]   */
+	uint32_t* tiles_touched;/* [P]     */
+	uint8_t* clamped;       /* [P,3]   */
+} GsbDebug;
+
+typedef struct GsbGrads {
+	float* dL_dmeans2D;     /* [P,3]  (z = 0)                         rasterize_points.cu:260 */
+	float* dL_dcolors;      /* [P,3]                                                     :261 */
+	float* dL_dopacity;     /* [P,1]  w.r.t. the raw logit                               :263 */
+	float* dL_dmeans3D;     /* [P,3]                                                     :259 */
+	float* dL_dcov3D;       /* [P,6]                                                     :264 */
+	float* dL_dsh;          /* [P,M,3] (NULL when M == 0)                                :265 */
+	float* dL_dscales;      /* [P,3]                                                     :266 */
+	float* dL_drotations;   /* [P,4]                                                     :267 */
+	float* dL_dconic;       /* [P,4] optional export (reference keeps it internal, :262); may be NULL */
+	int32_t accumulate;     /* 0: outputs are overwritten (no caller memset needed). 1: per-view gradients are ADDED
+	                           to the buffers (view-batch accumulation for the sharded multi-GPU path) */
+} GsbGrads;
+
+/* Sizes of the three scratch blobs, for callers that pre-allocate. */
+GSB_API size_t gsb_geom_bytes(int32_t P);
+GSB_API size_t gsb_image_bytes(int32_t width, int32_t height);
+GSB_API size_t gsb_binning_bytes(int64_t num_rendered);
+
+/* Forward.  Writes out_color [3,H,W] and radii [P]; *num_rendered [host] receives R.
+ * One stream synchronisation happens inside (the instance count sizes the binning blob, as in
+ * rasterizer_impl.cu:445-450); everything else is asynchronous on `stream`. */
+GSB_API int gsb_forward(const GsbScene* scene, const GsbCamera* cam,
+                gsb_alloc_fn geom_alloc, void* geom_user,
+                gsb_alloc_fn binning_alloc, void* binning_user,
+                gsb_alloc_fn image_alloc, void* image_user,
+                float* out_color, int32_t* radii, int64_t* num_rendered,
+                const GsbDebug* debug, void* stream);
+
+/* Backward from the blobs of the paired forward.  Fully asynchronous on `stream`. */
+GSB_API int gsb_backward(const GsbScene* scene, const GsbCamera* cam, int64_t num_rendered, const int32_t* radii,
+                 const char* geom_blob, const char* binning_blob, const char* image_blob,
+                 const float* dL_dout_color /* [3,H,W] */, const GsbGrads* grads,
+                 float lambda_sh_sparsity, void* stream);
+
+/* present[i] = view-space z of means3D[i] > 0.2 (auxiliary.h:139-159). */
+GSB_API int gsb_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* Decode pieces of the private blobs (test / tooling helpers; layouts are private and may change). */
+GSB_API int gsb_export_binning(const char* binning_blob, int64_t num_rendered, uint64_t* keys_sorted, uint32_t* point_list,
+                       void* stream);
+GSB_API int gsb_export_image(const char* image_blob, int32_t width, int32_t height, float* final_T, uint32_t* n_contrib,
+                     uint32_t* ranges /* [tiles,2] */, void* stream);
+
+/* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
+GSB_API uint64_t gsb_launch_count(void);
+
+GSB_API const char* gsb_last_error(void);
+GSB_API const char* gsb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS_B200_H_INCLUDED */

@@ -1,0 +1,175 @@
+// gsb_api.cu — the C ABI (include/gs_b200.h): orchestration of the forward / backward pipelines.
+//
+// Forward mirrors CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:359-504):
+//   preprocess -> scan -> [R to host, size the binning blob] -> emit keys -> radix sort -> tile ranges -> render
+// Backward mirrors Rasterizer::backward (rasterizer_impl.cu:508-630): render backward -> preprocess backward.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "gsb_common.cuh"
+
+namespace gsb {
+
+unsigned long long g_launch_count = 0;
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+	va_list ap; va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, int32_t*, const GsbDebug*, cudaStream_t);
+int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
+int launch_scan(const GeomState&, int, cudaStream_t);
+int launch_binning(const GeomState&, const BinningState&, char*, const ImageState&, int, long long, int, int, cudaStream_t);
+int launch_render_forward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, float*, cudaStream_t);
+int launch_render_backward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, const float*, float*, cudaStream_t);
+int launch_preprocess_backward(const GsbScene*, const GsbCamera*, const GeomState&, const int32_t*, const float*, const GsbGrads*, float, cudaStream_t);
+
+// geometry blob = GeomState followed by the backward's gradient accumulator (12 floats per Gaussian)
+static size_t geom_state_bytes(int P) { size_t b; GeomState::carve(nullptr, P, &b); return (b + 255) & ~size_t(255); }
+
+static int check_scene(const GsbScene* s, const GsbCamera* c)
+{
+	if (!s || !c) { set_error("scene / camera is NULL"); return GSB_EINVAL; }
+	if (s->P < 0) { set_error("P < 0"); return GSB_EINVAL; }
+	if (c->width <= 0 || c->height <= 0) { set_error("bad image size %dx%d", c->width, c->height); return GSB_EINVAL; }
+	if (!c->viewmatrix || !c->projmatrix || !c->campos || !c->background) { set_error("camera tensors missing"); return GSB_EINVAL; }
+	if (s->P == 0) return GSB_OK;
+	if (!s->means3D) { set_error("means3D missing"); return GSB_EINVAL; }
+	if (s->quant)
+	{
+		const GsbQuant* q = s->quant;
+		if (!q->ids_dc || !q->ids_rest || !q->ids_opacity || !q->ids_scaling || !q->ids_rot || !q->centers || !s->degrees)
+		{ set_error("quantised scene: id planes / centres / degrees missing"); return GSB_EINVAL; }
+		if (s->M != 16) { set_error("quantised scene needs M == 16"); return GSB_EINVAL; }
+		return GSB_OK;
+	}
+	if (!s->opacities) { set_error("opacities missing"); return GSB_EINVAL; }
+	// diff_gaussian_rasterization/__init__.py:203-207
+	if ((s->shs == nullptr) == (s->colors_precomp == nullptr)) { set_error("Please provide excatly one of either SHs or precomputed colors!"); return GSB_EINVAL; }
+	const bool sr = s->scales != nullptr && s->rotations != nullptr;
+	if (sr == (s->cov3D_precomp != nullptr) || ((s->scales != nullptr) != (s->rotations != nullptr)))
+	{ set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!"); return GSB_EINVAL; }
+	if (s->shs && !s->sh_packed && (!s->degrees || s->M <= 0)) { set_error("dense SH needs degrees and M > 0"); return GSB_EINVAL; }
+	return GSB_OK;
+}
+
+} // namespace gsb
+
+using namespace gsb;
+
+extern "C" {
+
+size_t gsb_geom_bytes(int32_t P) { return geom_state_bytes(P) + size_t(P) * 48 + 512; }
+size_t gsb_image_bytes(int32_t W, int32_t H) { size_t b; ImageState::carve(nullptr, W, H, &b); return b + 256; }
+size_t gsb_binning_bytes(int64_t R) { size_t b; BinningState::carve(nullptr, R, &b); return b + 256; }
+uint64_t gsb_launch_count(void) { return g_launch_count; }
+const char* gsb_last_error(void) { return g_err; }
+const char* gsb_version(void) { return "gs_b200 0.1 (sm_100a)"; }
+
+int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_alloc, void* geom_user,
+	gsb_alloc_fn binning_alloc, void* binning_user, gsb_alloc_fn image_alloc, void* image_user,
+	float* out_color, int32_t* radii, int64_t* num_rendered, const GsbDebug* debug, void* stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (int e = check_scene(scene, cam)) return e;
+	if (!out_color || !num_rendered || (scene->P > 0 && !radii)) { set_error("output pointers missing"); return GSB_EINVAL; }
+	*num_rendered = 0;
+	const int P = scene->P, W = cam->width, H = cam->height;
+	const size_t N = size_t(W) * H;
+	if (P == 0)
+	{
+		// rasterize_points.cu:170,184-185: P == 0 returns the zero-initialised image (no background)
+		GSB_CUDA_OK(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), stream));
+		return GSB_OK;
+	}
+	char* geom_blob = geom_alloc(geom_user, gsb_geom_bytes(P));
+	char* img_blob = image_alloc(image_user, gsb_image_bytes(W, H));
+	if (!geom_blob || !img_blob) { set_error("scratch allocation failed"); return GSB_ENOMEM; }
+	GeomState g = GeomState::carve(geom_blob, P);
+	ImageState img = ImageState::carve(img_blob, W, H);
+	GSB_CUDA_OK(cudaMemsetAsync(g.scan_state, 0, GeomState::scan_blocks(P) * sizeof(unsigned long long), stream));
+	GSB_CUDA_OK(cudaMemsetAsync(g.counters, 0, 16 * sizeof(uint32_t), stream));
+	if (int e = launch_preprocess(scene, cam, g, radii, debug, stream)) return e;
+	if (int e = launch_scan(g, P, stream)) return e;
+	// the instance count sizes the binning blob (rasterizer_impl.cu:445-450): one 16-byte read-back
+	static thread_local uint32_t* h_counters = nullptr;
+	if (!h_counters) GSB_CUDA_OK(cudaMallocHost(&h_counters, 16 * sizeof(uint32_t)));
+	GSB_CUDA_OK(cudaMemcpyAsync(h_counters, g.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	GSB_CUDA_OK(cudaStreamSynchronize(stream));
+	const long long R = h_counters[0];
+	if (h_counters[3]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSB_ECUDA; }
+	if (R >= (1ll << 30)) { set_error("%lld (Gaussian, tile) instances exceed the 2^30 limit of the sorter", R); return GSB_ERANGE; }
+	*num_rendered = R;
+	char* bin_blob = binning_alloc(binning_user, gsb_binning_bytes(R));
+	if (!bin_blob) { set_error("binning allocation failed"); return GSB_ENOMEM; }
+	BinningState b = BinningState::carve(bin_blob, R);
+	if (int e = launch_binning(g, b, bin_blob, img, P, R, W, H, stream)) return e;
+	if (int e = launch_render_forward(img, b, g, W, H, cam->background, out_color, stream)) return e;
+	return GSB_OK;
+}
+
+int gsb_backward(const GsbScene* scene, const GsbCamera* cam, int64_t R, const int32_t* radii,
+	const char* geom_blob, const char* binning_blob, const char* image_blob, const float* dL_dout_color,
+	const GsbGrads* grads, float lambda_sh_sparsity, void* stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (int e = check_scene(scene, cam)) return e;
+	if (!grads) { set_error("grads is NULL"); return GSB_EINVAL; }
+	const int P = scene->P, W = cam->width, H = cam->height;
+	if (P == 0) return GSB_OK;
+	if (!geom_blob || !binning_blob || !image_blob || !dL_dout_color || !radii) { set_error("backward inputs missing"); return GSB_EINVAL; }
+	if (!grads->dL_dmeans2D || !grads->dL_dcolors || !grads->dL_dopacity || !grads->dL_dmeans3D || !grads->dL_dcov3D ||
+		!grads->dL_dscales || !grads->dL_drotations || (scene->M > 0 && !grads->dL_dsh))
+	{ set_error("gradient output pointers missing"); return GSB_EINVAL; }
+	GeomState g = GeomState::carve(const_cast<char*>(geom_blob), P);
+	ImageState img = ImageState::carve(const_cast<char*>(image_blob), W, H);
+	BinningState b = BinningState::carve(const_cast<char*>(binning_blob), R);
+	float* acc = reinterpret_cast<float*>(const_cast<char*>(geom_blob) + geom_state_bytes(P));
+	GSB_CUDA_OK(cudaMemsetAsync(acc, 0, size_t(P) * 48, stream));
+	if (int e = launch_render_backward(img, b, g, W, H, cam->background, dL_dout_color, acc, stream)) return e;
+	if (int e = launch_preprocess_backward(scene, cam, g, radii, acc, grads, lambda_sh_sparsity, stream)) return e;
+	return GSB_OK;
+}
+
+int gsb_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present, void* stream)
+{
+	(void)projmatrix;
+	if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("mark_visible: bad arguments"); return GSB_EINVAL; }
+	return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+static __global__ void pick_sorted_kernel(const SortPlan* plan, const uint64_t* k0, const uint64_t* k1, const uint32_t* v0, const uint32_t* v1,
+	long long R, uint64_t* keys, uint32_t* vals)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= R) return;
+	const bool f = plan->final_buf != 0;
+	if (keys) keys[i] = f ? k1[i] : k0[i];
+	if (vals) vals[i] = f ? v1[i] : v0[i];
+}
+
+int gsb_export_binning(const char* binning_blob, int64_t R, uint64_t* keys_sorted, uint32_t* point_list, void* stream)
+{
+	if (R <= 0) return GSB_OK;
+	BinningState b = BinningState::carve(const_cast<char*>(binning_blob), R);
+	pick_sorted_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(b.plan, b.keys[0], b.keys[1], b.vals[0], b.vals[1], R, keys_sorted, point_list);
+	GSB_CUDA_OK(cudaGetLastError());
+	return GSB_OK;
+}
+
+int gsb_export_image(const char* image_blob, int32_t W, int32_t H, float* final_T, uint32_t* n_contrib, uint32_t* ranges, void* stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	ImageState img = ImageState::carve(const_cast<char*>(image_blob), W, H);
+	const size_t N = size_t(W) * H, T = size_t((W + 15) / 16) * ((H + 15) / 16);
+	if (final_T) GSB_CUDA_OK(cudaMemcpyAsync(final_T, img.final_T, N * 4, cudaMemcpyDeviceToDevice, stream));
+	if (n_contrib) GSB_CUDA_OK(cudaMemcpyAsync(n_contrib, img.n_contrib, N * 4, cudaMemcpyDeviceToDevice, stream));
+	if (ranges) GSB_CUDA_OK(cudaMemcpyAsync(ranges, img.ranges, T * 8, cudaMemcpyDeviceToDevice, stream));
+	return GSB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,307 @@
+// gsb_preprocess.cu — fused per-Gaussian forward preprocess (sm_100a).
+//
+// Replaces reference forward.cu:354-456 preprocessCUDA, forward.cu:246-350 variableSHPreprocessCUDA and
+// rasterizer_impl.cu:62-74 checkFrustum.  The reduced-3dgs extras are fused here so no PyTorch elementwise
+// pass runs: per-Gaussian variable-degree SH (dense or packed layout), codebook de-quantisation of u8
+// attribute ids (20 x 256 table staged in shared memory once per persistent block), and the prune mask.
+// One 48-byte render record per visible Gaussian is written (see gsb_common.cuh GeomState).
+#include "gsb_common.cuh"
+
+namespace gsb {
+
+struct PreArgs {
+	int P, M, W, H, gx, gy;
+	float mod, tan_fovx, tan_fovy, focal_x, focal_y;
+	const float* means3D; const float* opacities; const float* scales; const float* rotations;
+	const float* cov3D_precomp; const float* shs; const float* colors_precomp; const int32_t* degrees;
+	const float* view; const float* proj; const float* campos;
+	int packed; int cum[4]; long long group_base[4];   // packed SH: first vec3 index of each degree group
+	const uint8_t* prune;
+	int quant; GsbQuant q;
+	GeomState g; int32_t* radii;
+	GsbDebug dbg; int prefiltered;
+};
+
+// forward.cu:105-159 computeColorFromSH with the accumulation order of the reference build
+// (oracle/gs_oracle.cpp color_from_sh).  sh(k, c) returns coefficient k, channel c.
+template <class SH>
+__device__ __forceinline__ void sh_to_rgb(int deg, float x, float y, float z, SH sh, float* res)
+{
+#pragma unroll
+	for (int c = 0; c < 3; c++) res[c] = __fmul_rn(kSH_C0, sh(0, c));
+	if (deg > 0)
+	{
+		const float c1y = __fmul_rn(y, kSH_C1), c1z = __fmul_rn(z, kSH_C1), c1x = __fmul_rn(x, kSH_C1);
+#pragma unroll
+		for (int c = 0; c < 3; c++)
+		{
+			float t = __fmaf_rn(-c1y, sh(1, c), res[c]);
+			t = __fmaf_rn(c1z, sh(2, c), t);
+			res[c] = __fmaf_rn(-c1x, sh(3, c), t);
+		}
+		if (deg > 1)
+		{
+			const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+			const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+			const float zz2 = __fadd_rn(zz, zz);
+			const float w4 = __fmul_rn(xy, 1.0925484305920792f), w5 = __fmul_rn(yz, -1.0925484305920792f);
+			const float w6 = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), 0.31539156525252005f);
+			const float w7 = __fmul_rn(xz, -1.0925484305920792f), w8 = __fmul_rn(__fsub_rn(xx, yy), 0.5462742152960396f);
+#pragma unroll
+			for (int c = 0; c < 3; c++)
+			{
+				float t = __fmaf_rn(w4, sh(4, c), res[c]);
+				t = __fmaf_rn(w5, sh(5, c), t);
+				t = __fmaf_rn(w6, sh(6, c), t);
+				t = __fmaf_rn(w7, sh(7, c), t);
+				res[c] = __fmaf_rn(w8, sh(8, c), t);
+			}
+			if (deg > 2)
+			{
+				const float q = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);
+				const float w9 = __fmul_rn(__fmul_rn(y, -0.5900435899266435f), __fmaf_rn(xx, 3.0f, -yy));
+				const float w10 = __fmul_rn(__fmul_rn(xy, 2.890611442640554f), z);
+				const float w11 = __fmul_rn(__fmul_rn(y, -0.4570457994644658f), q);
+				const float w12 = __fmul_rn(__fmul_rn(z, 0.3731763325901154f), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));
+				const float w13 = __fmul_rn(__fmul_rn(x, -0.4570457994644658f), q);
+				const float w14 = __fmul_rn(__fmul_rn(z, 1.445305721320277f), __fsub_rn(xx, yy));
+				const float w15 = __fmul_rn(__fmul_rn(x, -0.5900435899266435f), __fmaf_rn(yy, -3.0f, xx));
+#pragma unroll
+				for (int c = 0; c < 3; c++)
+				{
+					float t = __fmaf_rn(w9, sh(9, c), res[c]);
+					t = __fmaf_rn(w10, sh(10, c), t);
+					t = __fmaf_rn(w11, sh(11, c), t);
+					t = __fmaf_rn(w12, sh(12, c), t);
+					t = __fmaf_rn(w13, sh(13, c), t);
+					t = __fmaf_rn(w14, sh(14, c), t);
+					res[c] = __fmaf_rn(w15, sh(15, c), t);
+				}
+			}
+		}
+	}
+}
+
+// Quaternion normalisation of the de-quantised rotation = torch.nn.functional.normalize(q) (gaussian_model.py:145-146
+// get_rotation): q / max(||q||, 1e-12) with ||q|| = sqrt(fma chain over the 4 squares).
+__device__ __forceinline__ void normalize_quat(float& r, float& x, float& y, float& z)
+{
+	float n2 = __fmul_rn(r, r);
+	n2 = __fmaf_rn(x, x, n2); n2 = __fmaf_rn(y, y, n2); n2 = __fmaf_rn(z, z, n2);
+	const float n = fmaxf(__fsqrt_rn(n2), 1e-12f);
+	r = __fdiv_rn(r, n); x = __fdiv_rn(x, n); y = __fdiv_rn(y, n); z = __fdiv_rn(z, n);
+}
+
+template <bool QUANT>
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
+{
+	extern __shared__ float s_cb[];   // QUANT: [20][256] centres; scaling row holds exp(centre)
+	if (QUANT)
+	{
+		for (int i = threadIdx.x; i < GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE; i += blockDim.x)
+		{
+			float v = a.q.centers[i];
+			if (i / GSB_CODEBOOK_SIZE == 17) v = exp_ref(v);      // get_scaling = exp(_scaling), gaussian_model.py:141-142
+			s_cb[i] = v;
+		}
+		__syncthreads();
+	}
+	unsigned block_vis = 0;
+	for (long long base = (long long)blockIdx.x * blockDim.x; base < a.P; base += (long long)gridDim.x * blockDim.x)
+	{
+		const long long idx = base + threadIdx.x;
+		bool visible = false;
+		if (idx < a.P)
+		{
+			uint32_t tiles = 0; int radius_i = 0;
+			uint2 rect = make_uint2(0, 0);
+			do {
+				if (a.prune && a.prune[idx]) break;                                   // pruned == culled
+				const float px = a.means3D[3 * idx], py = a.means3D[3 * idx + 1], pz = a.means3D[3 * idx + 2];
+				const float tz = xform_row(a.view, 2, px, py, pz);                    // auxiliary.h:139-159
+				if (tz <= 0.2f)
+				{
+					if (a.prefiltered) atomicExch(&a.g.counters[3], 1u);
+					break;
+				}
+				const float hx = xform_row(a.proj, 0, px, py, pz);
+				const float hy = xform_row(a.proj, 1, px, py, pz);
+				const float hw = xform_row(a.proj, 3, px, py, pz);
+				const float p_w = __frcp_rn(__fadd_rn(hw, 0.0000001f));
+				const float projx = __fmul_rn(hx, p_w), projy = __fmul_rn(hy, p_w);
+				float cov3D[6];
+				float opac_raw;
+				if (QUANT)
+				{
+					const uint8_t* is = a.q.ids_scaling + 3 * idx;
+					const uint8_t* ir = a.q.ids_rot + 4 * idx;
+					float r = s_cb[18 * 256 + ir[0]], x = s_cb[19 * 256 + ir[1]], y = s_cb[19 * 256 + ir[2]], z = s_cb[19 * 256 + ir[3]];
+					normalize_quat(r, x, y, z);
+					compute_cov3D(s_cb[17 * 256 + is[0]], s_cb[17 * 256 + is[1]], s_cb[17 * 256 + is[2]], a.mod, r, x, y, z, cov3D);
+					opac_raw = s_cb[16 * 256 + a.q.ids_opacity[idx]];
+				}
+				else
+				{
+					if (a.cov3D_precomp)
+					{
+#pragma unroll
+						for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[6 * idx + k];
+					}
+					else
+					{
+						const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+						compute_cov3D(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2], a.mod, q.x, q.y, q.z, q.w, cov3D);
+					}
+					opac_raw = a.opacities[idx];
+				}
+				const float opacity = sigmoid_ref(opac_raw);
+				const float tx = xform_row(a.view, 0, px, py, pz), ty = xform_row(a.view, 1, px, py, pz);
+				const float3 cov = compute_cov2D(tx, ty, tz, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, a.view);
+				const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));   // forward.cu:419
+				if (det == 0.0f) break;
+				const float det_inv = __frcp_rn(det);
+				const float conx = __fmul_rn(cov.z, det_inv), cony = __fmul_rn(-cov.y, det_inv), conz = __fmul_rn(cov.x, det_inv);
+				const float mid = __fmul_rn(0.5f, __fadd_rn(cov.x, cov.z));
+				const float sq = __fsqrt_rn(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
+				const float lambda1 = __fadd_rn(mid, sq), lambda2 = __fsub_rn(mid, sq);
+				const float my_radius = ceilf(__fmul_rn(3.0f, __fsqrt_rn(fmaxf(lambda1, lambda2))));
+				const float pix_x = ndc2pix(projx, a.W), pix_y = ndc2pix(projy, a.H);
+				uint2 rmin, rmax;
+				get_rect(pix_x, pix_y, (int)my_radius, a.gx, a.gy, rmin, rmax);
+				if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) break;
+				// ---- colour -------------------------------------------------------------------------
+				float rgb[3]; unsigned clamp_bits = 0;
+				if (a.colors_precomp)
+				{
+#pragma unroll
+					for (int c = 0; c < 3; c++) rgb[c] = a.colors_precomp[3 * idx + c];
+				}
+				else
+				{
+					const float dx0 = __fsub_rn(px, a.campos[0]), dy0 = __fsub_rn(py, a.campos[1]), dz0 = __fsub_rn(pz, a.campos[2]);
+					float l2 = __fmul_rn(dy0, dy0);
+					l2 = __fmaf_rn(dx0, dx0, l2); l2 = __fmaf_rn(dz0, dz0, l2);
+					const float len = __fsqrt_rn(l2);
+					const float dx = __fdiv_rn(dx0, len), dy = __fdiv_rn(dy0, len), dz = __fdiv_rn(dz0, len);
+					float res[3];
+					if (QUANT)
+					{
+						const int deg = a.degrees[idx];
+						const uint8_t* idc = a.q.ids_dc + 3 * idx;
+						const uint8_t* irest = a.q.ids_rest + 45 * idx;
+						sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) {
+							return k == 0 ? s_cb[idc[c]] : s_cb[k * 256 + irest[3 * (k - 1) + c]]; }, res);
+					}
+					else if (a.packed)
+					{
+						// forward.cu:19-36 getSHOffset: degree follows from the position in the degree-sorted list
+						int deg = 0;
+						if (idx >= a.cum[0]) deg = 1;
+						if (idx >= a.cum[1]) deg = 2;
+						if (idx >= a.cum[2]) deg = 3;
+						const long long first = deg == 0 ? 0 : a.cum[deg - 1];
+						const float* sh = a.shs + 3 * (a.group_base[deg] + (idx - first) * (long long)((deg + 1) * (deg + 1)));
+						sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) { return sh[3 * k + c]; }, res);
+					}
+					else
+					{
+						const float* sh = a.shs + 3 * idx * a.M;
+						sh_to_rgb(a.degrees[idx], dx, dy, dz, [&](int k, int c) { return sh[3 * k + c]; }, res);
+					}
+#pragma unroll
+					for (int c = 0; c < 3; c++)
+					{
+						const float v = __fadd_rn(res[c], 0.5f);
+						clamp_bits |= (v < 0.0f) ? (1u << c) : 0u;
+						rgb[c] = fmaxf(v, 0.0f);
+					}
+				}
+				// ---- stores -------------------------------------------------------------------------
+				radius_i = (int)my_radius;
+				tiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
+				rect = make_uint2(rmin.x | (rmax.x << 16), rmin.y | (rmax.y << 16));
+				const float pth = -__logf(255.0f * opacity);
+				float4* rec = a.g.rec + 3 * idx;
+				rec[0] = make_float4(conx, cony, conz, opacity);
+				rec[1] = make_float4(pix_x, pix_y, rgb[0], rgb[1]);
+				rec[2] = make_float4(rgb[2], tz, pth, 0.0f);
+				a.g.clamped[idx] = (uint8_t)clamp_bits;
+				visible = true;
+				if (a.dbg.depths) a.dbg.depths[idx] = tz;
+				if (a.dbg.means2D) { a.dbg.means2D[2 * idx] = pix_x; a.dbg.means2D[2 * idx + 1] = pix_y; }
+				if (a.dbg.cov3D) { for (int k = 0; k < 6; k++) a.dbg.cov3D[6 * idx + k] = cov3D[k]; }
+				if (a.dbg.conic_opacity) reinterpret_cast<float4*>(a.dbg.conic_opacity)[idx] = make_float4(conx, cony, conz, opacity);
+				if (a.dbg.rgb) { for (int c = 0; c < 3; c++) a.dbg.rgb[3 * idx + c] = rgb[c]; }
+				if (a.dbg.clamped) { for (int c = 0; c < 3; c++) a.dbg.clamped[3 * idx + c] = (clamp_bits >> c) & 1u; }
+			} while (false);
+			a.radii[idx] = radius_i;
+			a.g.tiles_touched[idx] = tiles;
+			a.g.rect[idx] = rect;
+			if (a.dbg.tiles_touched) a.dbg.tiles_touched[idx] = tiles;
+		}
+		block_vis += __popc(__ballot_sync(0xffffffffu, visible)) * ((threadIdx.x & 31) == 0);
+	}
+	// number of visible Gaussians (SH-sparsity multiplier, rasterizer_impl.cu:549-571) without a later reduction pass
+	if ((threadIdx.x & 31) == 0 && block_vis) atomicAdd(&a.g.counters[1], block_vis);
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view, uint8_t* __restrict__ present)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P) return;
+	present[idx] = xform_row(view, 2, means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]) > 0.2f;
+}
+
+int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& g, int32_t* radii, const GsbDebug* dbg, cudaStream_t stream)
+{
+	PreArgs a{};
+	a.P = s->P; a.M = s->M; a.W = cam->width; a.H = cam->height;
+	a.gx = (cam->width + GSB_TILE_X - 1) / GSB_TILE_X; a.gy = (cam->height + GSB_TILE_Y - 1) / GSB_TILE_Y;
+	a.mod = s->scale_modifier; a.tan_fovx = cam->tan_fovx; a.tan_fovy = cam->tan_fovy;
+	a.focal_y = cam->height / (2.0f * cam->tan_fovy);                                    // rasterizer_impl.cu:386-387
+	a.focal_x = cam->width / (2.0f * cam->tan_fovx);
+	a.means3D = s->means3D; a.opacities = s->opacities; a.scales = s->scales; a.rotations = s->rotations;
+	a.cov3D_precomp = s->cov3D_precomp; a.shs = s->shs; a.colors_precomp = s->colors_precomp; a.degrees = s->degrees;
+	a.view = cam->viewmatrix; a.proj = cam->projmatrix; a.campos = cam->campos;
+	a.packed = s->sh_packed;
+	if (s->sh_packed)
+	{
+		long long cum = 0, base = 0;
+		for (int d = 0; d < 4; d++)
+		{
+			a.group_base[d] = base;
+			base += (long long)s->band_count[d] * (d + 1) * (d + 1);
+			cum += s->band_count[d];
+			a.cum[d] = (int)cum;
+		}
+	}
+	a.prune = s->prune_mask;
+	a.quant = s->quant != nullptr;
+	if (s->quant) a.q = *s->quant;
+	a.g = g; a.radii = radii;
+	if (dbg) a.dbg = *dbg;
+	a.prefiltered = cam->prefiltered;
+	const int blocks_needed = (s->P + 255) / 256;
+	if (a.quant)
+	{
+		const int smem = GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE * sizeof(float);
+		const int grid = blocks_needed < 148 * 8 ? blocks_needed : 148 * 8;               // persistent: amortise the table load
+		preprocess_kernel<true><<<grid, 256, smem, stream>>>(a);
+	}
+	else
+		preprocess_kernel<false><<<blocks_needed, 256, 0, stream>>>(a);
+	GSB_LAUNCHED();
+	GSB_CUDA_OK(cudaGetLastError());
+	return GSB_OK;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t stream)
+{
+	if (P <= 0) return GSB_OK;
+	mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, view, present);
+	GSB_LAUNCHED();
+	GSB_CUDA_OK(cudaGetLastError());
+	return GSB_OK;
+}
+
+} // namespace gsb

@@ -1,0 +1,199 @@
+"""Drop-in for the reference's pybind module `diff_gaussian_rasterization._C` (ext.cpp:17-20), re-hosted on the
+C ABI of include/gs_b200.h through ctypes.  Same function names, positional signatures, return tuples and error
+behaviour as rasterize_points.h:18-93; tensors in, torch.Tensors out.
+
+Build-defined extensions (keyword-only): `prune_mask` (u8/bool [P], 1 = pruned), `quant`
+(a gs_b200.synth.QuantScene-like object with u8 id planes + [20,256] centres) and `debug_out` (dict that
+receives the forward intermediates in the reference's GeometryState layouts).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from gs_b200 import lib as _lib
+from gs_b200.lib import GsbCamera, GsbDebug, GsbGrads, GsbQuant, GsbScene, BlobAllocator, f32, ptr
+
+
+def _device_of(means3D: torch.Tensor) -> torch.device:
+    if not means3D.is_cuda:
+        raise RuntimeError("gs_b200: means3D must live on a CUDA device (no CPU path exists)")
+    return means3D.device
+
+
+def _camera(device, bg, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, prefiltered, keep):
+    bg, viewmatrix, projmatrix, campos = (f32(bg, device), f32(viewmatrix, device), f32(projmatrix, device),
+                                           f32(campos, device))
+    keep += [bg, viewmatrix, projmatrix, campos]
+    return GsbCamera(int(W), int(H), float(tan_fovx), float(tan_fovy), ptr(viewmatrix), ptr(projmatrix), ptr(campos),
+                     ptr(bg), int(bool(prefiltered)))
+
+
+def _quant_struct(quant, device, keep):
+    def u8(t):
+        t = t.to(device=device, dtype=torch.uint8).contiguous()
+        keep.append(t)
+        return t.data_ptr()
+    centers = f32(quant.centers, device)
+    keep.append(centers)
+    q = GsbQuant(u8(quant.ids_dc), u8(quant.ids_rest), u8(quant.ids_opacity), u8(quant.ids_scaling), u8(quant.ids_rot),
+                 centers.data_ptr())
+    keep.append(q)
+    return C.pointer(q)
+
+
+def _scene(device, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, sh, degrees, keep,
+           packed_counts=None, prune_mask=None, quant=None):
+    means3D = f32(means3D, device)
+    P = int(means3D.shape[0]) if means3D is not None else 0
+    colors, opacity, scales, rotations = f32(colors, device), f32(opacity, device), f32(scales, device), f32(rotations, device)
+    cov3D_precomp, sh = f32(cov3D_precomp, device), f32(sh, device)
+    if degrees is not None and degrees.numel() > 0:
+        degrees = degrees.to(device=device, dtype=torch.int32).contiguous()
+    else:
+        degrees = None
+    if prune_mask is not None:
+        prune_mask = prune_mask.to(device=device, dtype=torch.uint8).contiguous()
+    keep += [means3D, colors, opacity, scales, rotations, cov3D_precomp, sh, degrees, prune_mask]
+    M = 0
+    if quant is not None:
+        M = 16
+    elif sh is not None and packed_counts is None:
+        M = int(sh.shape[1])                                       # rasterize_points.cu:187-191
+    s = GsbScene()
+    s.P, s.M = P, M
+    s.means3D, s.opacities, s.scales, s.rotations = ptr(means3D), ptr(opacity), ptr(scales), ptr(rotations)
+    s.cov3D_precomp, s.shs, s.colors_precomp, s.degrees = ptr(cov3D_precomp), ptr(sh), ptr(colors), ptr(degrees)
+    s.scale_modifier = float(scale_modifier)
+    s.sh_packed = 0
+    if packed_counts is not None:
+        s.sh_packed = 1
+        for d in range(4):
+            s.band_count[d] = int(packed_counts[d]) if d < len(packed_counts) else 0
+    s.prune_mask = ptr(prune_mask)
+    s.quant = _quant_struct(quant, device, keep) if quant is not None else None
+    return s, P, M
+
+
+def _forward(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix,
+             tan_fovx, tan_fovy, image_height, image_width, sh, degrees, campos, prefiltered, debug, packed_counts=None,
+             prune_mask=None, quant=None, debug_out=None):
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")          # rasterize_points.cu:158-161
+    device = _device_of(means3D)
+    L = _lib.lib()
+    keep = []
+    H, W = int(image_height), int(image_width)
+    with torch.cuda.device(device):
+        scene, P, M = _scene(device, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, sh, degrees,
+                             keep, packed_counts, prune_mask, quant)
+        cam = _camera(device, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, prefiltered, keep)
+        out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+        radii = torch.empty((P,), dtype=torch.int32, device=device)
+        geom, binning, img = BlobAllocator(device), BlobAllocator(device), BlobAllocator(device)
+        dbg_ptr = None
+        if debug_out is not None:
+            d = dict(depths=torch.zeros(P, device=device), means2D=torch.zeros(P, 2, device=device),
+                     cov3D=torch.zeros(P, 6, device=device), conic_opacity=torch.zeros(P, 4, device=device),
+                     rgb=torch.zeros(P, 3, device=device), tiles_touched=torch.zeros(P, dtype=torch.int32, device=device),
+                     clamped=torch.zeros(P, 3, dtype=torch.uint8, device=device))
+            debug_out.update(d)
+            dbg = GsbDebug(*[ptr(d[k]) for k in ("depths", "means2D", "cov3D", "conic_opacity", "rgb", "tiles_touched", "clamped")])
+            dbg_ptr = C.pointer(dbg)
+        R = C.c_int64(0)
+        st = L.gsb_forward(C.byref(scene), C.byref(cam), geom.cb, None, binning.cb, None, img.cb, None,
+                           out_color.data_ptr(), ptr(radii), C.byref(R), dbg_ptr, _lib.current_stream(device))
+        _lib.check(st)
+        if debug:
+            torch.cuda.synchronize(device)                      # reference CHECK_CUDA(debug) semantics, auxiliary.h:161-168
+    return int(R.value), out_color, radii, geom.tensor, binning.tensor, img.tensor
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                        projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degrees, campos, prefiltered, debug,
+                        *, prune_mask=None, quant=None, debug_out=None):
+    """rasterize_points.h:43-63 RasterizeGaussiansCUDA -> (R, color, radii, geomBuffer, binningBuffer, imgBuffer)."""
+    return _forward(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                    projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degrees, campos, prefiltered, debug,
+                    None, prune_mask, quant, debug_out)
+
+
+def rasterize_gaussians_variableSH_bands(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
+                                         perBandPrimitiveCount, cumSumPrimitiveCount, coeffsNum, degrees, campos, prefiltered,
+                                         debug, *, prune_mask=None, debug_out=None):
+    """rasterize_points.h:18-41 RasterizeGaussiansVariableSHBandsCUDA (inference, packed per-degree SH groups).
+    cumSumPrimitiveCount / coeffsNum are implied by perBandPrimitiveCount ([1,4,9,16] per gaussian_renderer:90-92)."""
+    counts = [int(v) for v in perBandPrimitiveCount.detach().cpu().tolist()]
+    return _forward(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                    projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degrees, campos, prefiltered, debug,
+                    counts, prune_mask, None, debug_out)
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                                 projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degrees, campos, geomBuffer, R,
+                                 binningBuffer, imageBuffer, lambda_sh_sparsity, debug, *, prune_mask=None, quant=None,
+                                 accumulate_into=None, want_conic=False):
+    """rasterize_points.h:65-88 RasterizeGaussiansBackwardCUDA ->
+    (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations).
+    `accumulate_into`: the same 8-tuple from a previous call; gradients are added in place (view-batch accumulation)."""
+    device = _device_of(means3D)
+    L = _lib.lib()
+    keep = []
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    with torch.cuda.device(device):
+        scene, P, M = _scene(device, means3D, colors, None, scales, rotations, scale_modifier, cov3D_precomp, sh, degrees, keep,
+                             None, prune_mask, quant)
+        if quant is None:
+            scene.opacities = means3D.data_ptr() if P > 0 else None      # not read by the backward; keeps check_scene satisfied
+        cam = _camera(device, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, False, keep)
+        dL = f32(dL_dout_color, device)
+        if accumulate_into is not None:
+            outs = list(accumulate_into)
+        else:
+            e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+            outs = [e(P, 3), e(P, 3), e(P, 1), e(P, 3), e(P, 6), e(P, M, 3), e(P, 3), e(P, 4)]
+        conic = torch.empty((P, 4), dtype=torch.float32, device=device) if want_conic else None
+        g = GsbGrads(ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), ptr(outs[4]), ptr(outs[5]), ptr(outs[6]), ptr(outs[7]),
+                     ptr(conic), 1 if accumulate_into is not None else 0)
+        radii = radii.to(device=device, dtype=torch.int32).contiguous()
+        st = L.gsb_backward(C.byref(scene), C.byref(cam), int(R), ptr(radii), ptr(geomBuffer), ptr(binningBuffer),
+                            ptr(imageBuffer), ptr(dL), C.byref(g), float(lambda_sh_sparsity), _lib.current_stream(device))
+        _lib.check(st)
+        if debug:
+            torch.cuda.synchronize(device)
+    if want_conic:
+        return tuple(outs) + (conic,)
+    return tuple(outs)
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """rasterize_points.h:90-93 markVisible -> bool[P]."""
+    device = _device_of(means3D)
+    P = int(means3D.size(0))
+    present = torch.zeros((P,), dtype=torch.bool, device=device)
+    if P:
+        m, v, p = f32(means3D, device), f32(viewmatrix, device), f32(projmatrix, device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().gsb_mark_visible(P, ptr(m), ptr(v), ptr(p), present.data_ptr(), _lib.current_stream(device)))
+    return present
+
+
+def export_state(geomBuffer, binningBuffer, imageBuffer, R, W, H):
+    """Decode the private blobs into reference-layout arrays (tests / tooling)."""
+    device = imageBuffer.device
+    L = _lib.lib()
+    out = {}
+    with torch.cuda.device(device):
+        keys = torch.zeros(max(R, 0), dtype=torch.int64, device=device)
+        pl = torch.zeros(max(R, 0), dtype=torch.int32, device=device)
+        if R > 0:
+            _lib.check(L.gsb_export_binning(ptr(binningBuffer), int(R), ptr(keys), ptr(pl), _lib.current_stream(device)))
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        final_T = torch.zeros(H, W, device=device)
+        n_contrib = torch.zeros(H, W, dtype=torch.int32, device=device)
+        ranges = torch.zeros(T, 2, dtype=torch.int32, device=device)
+        _lib.check(L.gsb_export_image(ptr(imageBuffer), W, H, ptr(final_T), ptr(n_contrib), ptr(ranges), _lib.current_stream(device)))
+    out.update(keys=keys, point_list=pl, final_T=final_T, n_contrib=n_contrib, ranges=ranges)
+    return out

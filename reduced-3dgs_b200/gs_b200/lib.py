@@ -1,0 +1,150 @@
+"""ctypes binding of libgs_b200.so (C ABI: include/gs_b200.h).
+
+This is the only bridge between the Python host side and the CUDA library.  There is NO fallback: if the
+library is missing or no CUDA device is present, calls raise.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libgs_b200.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class GsbQuant(C.Structure):
+    _fields_ = [("ids_dc", C.c_void_p), ("ids_rest", C.c_void_p), ("ids_opacity", C.c_void_p),
+                ("ids_scaling", C.c_void_p), ("ids_rot", C.c_void_p), ("centers", C.c_void_p)]
+
+
+class GsbScene(C.Structure):
+    _fields_ = [("P", C.c_int32), ("M", C.c_int32), ("means3D", C.c_void_p), ("opacities", C.c_void_p),
+                ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("shs", C.c_void_p),
+                ("colors_precomp", C.c_void_p), ("degrees", C.c_void_p), ("scale_modifier", C.c_float),
+                ("sh_packed", C.c_int32), ("band_count", C.c_int32 * 4), ("prune_mask", C.c_void_p),
+                ("quant", C.POINTER(GsbQuant))]
+
+
+class GsbCamera(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("background", C.c_void_p), ("prefiltered", C.c_int32)]
+
+
+class GsbDebug(C.Structure):
+    _fields_ = [("depths", C.c_void_p), ("means2D", C.c_void_p), ("cov3D", C.c_void_p), ("conic_opacity", C.c_void_p),
+                ("rgb", C.c_void_p), ("tiles_touched", C.c_void_p), ("clamped", C.c_void_p)]
+
+
+class GsbGrads(C.Structure):
+    _fields_ = [("dL_dmeans2D", C.c_void_p), ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p),
+                ("dL_dmeans3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p),
+                ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p), ("dL_dconic", C.c_void_p),
+                ("accumulate", C.c_int32)]
+
+
+_lib = None
+
+
+def ensure_built() -> str:
+    """Compile the library if it is absent or stale (needs nvcc; the GPU box uses the shipped .so)."""
+    src_dir = os.path.join(os.path.dirname(HERE), "csrc")
+    if os.path.isfile(os.path.join(src_dir, "build.py")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("gsb_build", os.path.join(src_dir, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        try:
+            return mod.build()
+        except (RuntimeError, FileNotFoundError):
+            if os.path.isfile(SO_PATH):
+                return SO_PATH
+            raise
+    return SO_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = ensure_built()
+        if not os.path.isfile(path):
+            raise RuntimeError(f"gs_b200: CUDA library {path} is missing — build it with reduced-3dgs_b200/csrc/build.py "
+                               "(there is no CPU / PyTorch fallback)")
+        L = C.CDLL(path)
+        L.gsb_geom_bytes.restype = C.c_size_t
+        L.gsb_geom_bytes.argtypes = [C.c_int32]
+        L.gsb_image_bytes.restype = C.c_size_t
+        L.gsb_image_bytes.argtypes = [C.c_int32, C.c_int32]
+        L.gsb_binning_bytes.restype = C.c_size_t
+        L.gsb_binning_bytes.argtypes = [C.c_int64]
+        L.gsb_launch_count.restype = C.c_uint64
+        L.gsb_last_error.restype = C.c_char_p
+        L.gsb_version.restype = C.c_char_p
+        L.gsb_forward.restype = C.c_int
+        L.gsb_forward.argtypes = [C.POINTER(GsbScene), C.POINTER(GsbCamera), ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p,
+                                  ALLOC_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                  C.POINTER(GsbDebug), C.c_void_p]
+        L.gsb_backward.restype = C.c_int
+        L.gsb_backward.argtypes = [C.POINTER(GsbScene), C.POINTER(GsbCamera), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.POINTER(GsbGrads), C.c_float, C.c_void_p]
+        L.gsb_mark_visible.restype = C.c_int
+        L.gsb_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsb_export_binning.restype = C.c_int
+        L.gsb_export_binning.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsb_export_image.restype = C.c_int
+        L.gsb_export_image.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = ["gsb_geom_bytes", "gsb_image_bytes", "gsb_binning_bytes", "gsb_forward", "gsb_backward",
+                    "gsb_mark_visible", "gsb_export_binning", "gsb_export_image", "gsb_launch_count", "gsb_last_error",
+                    "gsb_version"]
+
+
+def check(status: int):
+    if status != 0:
+        raise RuntimeError("gs_b200: " + lib().gsb_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(lib().gsb_launch_count())
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor; None / empty tensors are the reference's "absent" (NULL)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
+    """Reference L1 contract: fp32, contiguous, on the CUDA device (rasterize_points.cu:197-217 .contiguous())."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+class BlobAllocator:
+    """Python side of gsb_alloc_fn: allocates a torch uint8 tensor (the reference's resizeFunctional,
+    rasterize_points.cu:33-41) and keeps it so it can be returned to the caller."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self.tensor.data_ptr()
+
+
+def current_stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
