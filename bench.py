@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py — rendered Mpixels/s, forward+backward, of the splat-rasterizer hot path on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # our CUDA path (default workload C2)
+    python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 # the unmodified reference rasterizer (oracle/_ref)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one view: forward (preprocess -> binning -> sort -> composite) + backward, on synthetic data of the
+BASELINE.json configuration (default C2 = configs[1]: 500k Gaussians, SH degree 3, 1920x1080).  Prints ONE JSON line.
+
+  value   whole-job Mpix/s with inputs resident in HBM; every step is timed with its own CUDA-event pair on the
+          stream the kernels run on, L2 is flushed (256 MB write) between steps outside the event pairs
+  e2e     the same metric through the reference-facing public API (gaussian_renderer.render + autograd) with the
+          step's inputs (camera matrices, dL/dimage) copied from pinned host memory and the loss read back
+  roofline  dominant kernel: SURVEY.md §8(d) algorithmic bytes / its CUDA-event time (measured live, in the timed
+          region, by the library's per-kernel event pairs) against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (port of the reference arithmetic, all host cores) on one view of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "reduced-3dgs_b200"))
+from gs_b200 import synth  # noqa: E402
+
+EMPTY = torch.Tensor([])
+
+
+# ------------------------------------------------------------------------------------------------------
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--points", type=int, default=0, help="override the number of Gaussians (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def physical_gpu_index(local: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    parts = [p for p in vis.split(",") if p.strip()]
+    if local < len(parts) and parts[local].strip().isdigit():
+        return int(parts[local])
+    return local
+
+
+def bench_cameras(W, H, n=16):
+    """Views around the canonical camera: small yaw steps so every view sees the whole cloud."""
+    cams = []
+    for i in range(n):
+        th = math.radians((i - n / 2) * 1.5)
+        Rc2w = np.array([[math.cos(th), 0, math.sin(th)], [0, 1, 0], [-math.sin(th), 0, math.cos(th)]])
+        C = Rc2w @ np.array([0.0, 0.0, -4.0])
+        cams.append(synth.make_camera(W, H, Rc2w, -Rc2w.T @ C))
+    return cams
+
+
+class ModelView:
+    """Duck-typed stand-in for the reference GaussianModel (the attributes gaussian_renderer.render reads)."""
+
+    def __init__(self, scene, dev, quant=None, prune_mask=None):
+        self._xyz = scene.means3D.to(dev).requires_grad_(True)
+        self._opacity = scene.opacity.to(dev).requires_grad_(quant is None)
+        self._scaling = scene.scales.to(dev).requires_grad_(quant is None)
+        self._rotation = scene.rotations.to(dev).requires_grad_(quant is None)
+        self._features = scene.sh.to(dev).requires_grad_(quant is None)
+        self._degrees = scene.degrees.to(dev)
+        self.active_sh_degree = self.max_sh_degree = 3
+        self.quant, self.prune_mask = quant, prune_mask
+        self.per_band_count = [int((scene.degrees == d).sum()) for d in range(4)]
+
+    get_xyz = property(lambda s: s._xyz)
+    get_scaling = property(lambda s: s._scaling)
+    get_rotation = property(lambda s: s._rotation)
+    get_features = property(lambda s: s._features)
+
+    def params(self):
+        return [self._xyz, self._opacity, self._scaling, self._rotation, self._features]
+
+
+def algorithmic_bytes(P, V, R, sumK, Npx, Nt, rho_f, rho_b, quant, mask):
+    """SURVEY.md §8(d) formulas (bytes per frame)."""
+    if quant:
+        pre_in = P * (12 + 11 + 4) + 3 * max(sumK - V, 0) + 20 * 1024
+    else:
+        pre_in = P * 48 + 12 * sumK
+    B_pre = pre_in + (P if mask else 0) + V * 40 + P * 8
+    B_bin = P * 8 + P * 4 + V * 16 + R * 12 + R * 24 + R * 4 + Nt * 8
+    B_rend = R * 40 * rho_f + Npx * 20
+    B_bwdR = R * 40 * rho_b + Npx * 20 + V * 36 * 2
+    B_bwdP = V * (12 + 24 + 12 + 16 + 16 + 3) + 12 * sumK * 2 + V * (12 + 12 + 16 + 4) + P * 12
+    return dict(preprocess=B_pre, binning=B_bin, render_forward=B_rend, render_backward=B_bwdR, preprocess_backward=B_bwdP)
+
+
+# ------------------------------------------------------------------------------------------------------
+def build_workload(args, dev, rank, world):
+    name = args.config
+    W, H = synth.config_image(name)
+    scene = synth.config_scene(name, args.points or None)
+    quant = prune = None
+    if name in ("C3", "C4", "C5"):
+        quant = synth.quantise_scene(scene, seed=0)
+        scene = quant.dequantise()          # the fp32 tensors the reference sees (load_ply de-quantises once)
+    if name == "C4":
+        prune = synth.prune_mask(scene.P, 4)
+    return name, W, H, scene, quant, prune
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.impl == "reference" and rank != 0:
+        return 0                                    # the reference is single-GPU: rank 0 alone runs it
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    name, W, H, scene, quant, prune = build_workload(args, dev, rank, world)
+    Npx = W * H
+    cams = [c.to(dev) for c in bench_cameras(W, H)]
+    my_views = list(range(rank, len(cams), world)) if args.impl == "ours" else list(range(len(cams)))
+    bg = torch.zeros(3, device=dev)
+    G_host = synth.grad_image(W, H, 1000 + rank).pin_memory()
+    G = G_host.to(dev)
+    tanx = [math.tan(c.FoVx * 0.5) for c in cams]
+    tany = [math.tan(c.FoVy * 0.5) for c in cams]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    K, Wm = args.steps, args.warmup
+
+    sd = scene.to(dev)
+    prune_d = None if prune is None else prune.to(dev)
+    refC = None
+    if args.impl == "ours":
+        from diff_gaussian_rasterization import _C
+        from gs_b200 import lib as gsl
+        from gs_b200 import multi
+        qd = None if quant is None else quant.to(dev)
+        if world > 1:      # replicate the scene from rank 0 (the only model-state transfer of the sharded path)
+            multi.broadcast_scene([sd.means3D, sd.opacity, sd.scales, sd.rotations, sd.sh])
+        acc = multi.GradAccumulator(sd.P, 16 if qd is not None else sd.sh.shape[1], dev) if world > 1 else None
+
+        def step(i, dL):
+            v = my_views[i % len(my_views)]
+            c = cams[v]
+            if qd is not None:
+                a = (bg, sd.means3D, EMPTY, EMPTY, EMPTY, EMPTY, 1.0, EMPTY, c.world_view_transform, c.full_proj_transform,
+                     tanx[v], tany[v], H, W, EMPTY, sd.degrees, c.camera_center, False, False)
+            else:
+                a = (bg, sd.means3D, EMPTY, sd.opacity, sd.scales, sd.rotations, 1.0, EMPTY, c.world_view_transform,
+                     c.full_proj_transform, tanx[v], tany[v], H, W, sd.sh, sd.degrees, c.camera_center, False, False)
+            R, color, radii, gb, bb, ib = _C.rasterize_gaussians(*a, prune_mask=prune_d, quant=qd)
+            grads = _C.rasterize_gaussians_backward(bg, sd.means3D, radii, EMPTY, a[4], a[5], 1.0, EMPTY, a[8], a[9], a[10], a[11],
+                                                    dL, a[14], sd.degrees, a[16], gb, R, bb, ib, 0.0, False, prune_mask=prune_d,
+                                                    quant=qd, accumulate_into=None if acc is None else acc.buffers())
+            return R, color, radii, ib, grads
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import build_ref
+        refC = build_ref.load()
+        if refC is None:
+            return reference_cpu_port(args, name, W, H, scene, cams, tanx, tany)
+        ref_scene = sd.compact(~prune_d.bool()) if prune_d is not None else sd   # reference semantics of pruning: delete rows
+
+        def step(i, dL):
+            v = my_views[i % len(my_views)]
+            c = cams[v]
+            s = ref_scene
+            a = (bg, s.means3D, EMPTY, s.opacity, s.scales, s.rotations, 1.0, EMPTY, c.world_view_transform, c.full_proj_transform,
+                 tanx[v], tany[v], H, W, s.sh, s.degrees, c.camera_center, False, False)
+            R, color, radii, gb, bb, ib = refC.rasterize_gaussians(*a)
+            grads = refC.rasterize_gaussians_backward(bg, s.means3D, radii, EMPTY, s.scales, s.rotations, 1.0, EMPTY, a[8], a[9],
+                                                      a[10], a[11], dL, s.sh, s.degrees, a[16], gb, R, bb, ib, 0.0, False)
+            return R, color, radii, ib, grads
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1 and args.impl == "ours":
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident measurement (`value`) ----------------
+    for i in range(max(Wm, 3)):
+        out = step(i, G)
+    R0, color0, radii0, ib0, _ = out
+    torch.cuda.synchronize()
+    if args.impl == "ours":
+        gsl.profile_enable(True)
+        gsl.profile_read()
+        launches0 = gsl.launch_count()
+    sampler = ClockSampler(physical_gpu_index(local))
+    barrier()
+    if rank == 0:
+        sampler.start()
+    evs = []
+    for i in range(K):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = step(i, G)
+        e1.record()
+        evs.append((e0, e1))
+    coll_ms = 0.0
+    if world > 1 and args.impl == "ours":
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        acc.all_reduce()                       # one gradient all-reduce closes the K-view batch
+        e1.record()
+        torch.cuda.synchronize()
+        coll_ms = e0.elapsed_time(e1)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(step_ms) + coll_ms
+    if world > 1 and args.impl == "ours":
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    n_gpus = world if args.impl == "ours" else 1
+    value = n_gpus * K * Npx / (total_ms * 1e-3) / 1e6
+    prof, launches = {}, None
+    if args.impl == "ours":
+        prof = gsl.profile_read()
+        gsl.profile_enable(False)
+        launches = gsl.launch_count() - launches0
+
+    # ---------------- end-to-end through the public API with host buffers (`e2e`) ----------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, H, W, K, flush, refC, world, n_gpus, rank)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return 0
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_src = peaks()
+    radii_t = radii0
+    V = int((radii_t > 0).sum())
+    deg = sd.degrees.view(-1)[: radii_t.shape[0]] if args.impl == "ours" else None
+    roof = None
+    if args.impl == "ours":
+        from diff_gaussian_rasterization import _C as _C2
+        sumK = int((((deg.long() + 1) ** 2)[radii_t > 0]).sum())
+        st = _C2.export_state(None, None, ib0, 0, W, H)
+        ncon = st["n_contrib"].float()[None, None]
+        tile_max = torch.nn.functional.max_pool2d(ncon, 16, ceil_mode=True)
+        rho = float(tile_max.sum().item()) / max(R0, 1)
+        Nt = ((W + 15) // 16) * ((H + 15) // 16)
+        B = algorithmic_bytes(sd.P, V, R0, sumK, Npx, Nt, rho, rho, quant is not None, prune is not None)
+        groups = {"preprocess": ["preprocess"], "binning": ["scan", "emit_keys", "sort_hist", "sort_plan", "sort_pass", "tile_ranges"],
+                  "render_forward": ["render_forward"], "render_backward": ["render_backward"], "preprocess_backward": ["preprocess_backward"]}
+        per_kernel = {k: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K} for k, v in prof.items()}
+        stage_ms = {g: sum(prof.get(k, (0, 0))[0] for k in ks) / K for g, ks in groups.items()}
+        dom = max(["render_forward", "render_backward", "preprocess", "preprocess_backward"], key=lambda g: stage_ms[g])
+        ach = B[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+        frame_bytes = sum(B.values())
+        kern_ms = sum(stage_ms.values())
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes": int(B[dom]), "kernel_ms": round(stage_ms[dom], 4),
+                "stages": {g: {"ms": round(stage_ms[g], 4), "alg_MB": round(B[g] / 1e6, 1),
+                               "GBps": round(B[g] / max(stage_ms[g], 1e-9) / 1e6, 1),
+                               "frac": round(B[g] / max(stage_ms[g], 1e-9) / 1e6 / peak, 4)} for g in groups},
+                "frame": {"alg_MB": round(frame_bytes / 1e6, 1), "kernel_ms": round(kern_ms, 4),
+                          "frac": round(frame_bytes / max(kern_ms, 1e-9) / 1e6 / peak, 4)},
+                "rho_list_consumed": round(rho, 4), "kernels": per_kernel}
+
+    # ---------------- CPU baseline: the oracle on the host cores, one view of the same workload ----------------
+    cpu = None
+    if args.impl == "ours" and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(scene, prune, cams[0].to("cpu"), W, H)
+
+    line = {"metric": "rendered Mpixels/s fwd+bwd", "value": round(value, 2), "unit": "Mpix/s", "n_gpus": n_gpus, "steps": K,
+            "warmup": max(Wm, 3), "ms_per_step": round(total_ms / K, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}: {scene.P} Gaussians, {W}x{H}, fwd+bwd, one view per step"
+                                   + (", codebook-quantised (fused dequant)" if (quant is not None and args.impl == 'ours') else "")
+                                   + (", prune mask" if prune is not None else ""),
+                       "points": scene.P, "image": [W, H], "visible": V, "instances_R": int(R0),
+                       "l2": "256 MB flush write between steps (outside the per-step event pairs)",
+                       "parallelism": f"views sharded over {n_gpus} GPU(s), scene replicated"
+                                      + (", one gradient all-reduce per K-view batch" if n_gpus > 1 else "")},
+            "impl": args.impl, "clocks": clocks}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if launches is not None:
+        line["gpu_launches"] = int(launches)
+    if roof is not None:
+        line["roofline"] = roof
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if args.impl == "reference":
+        line["cpu_baseline"] = {"value": line["value"], "unit": "Mpix/s", "cores": 0, "kind": "reference",
+                                "sample": "the reference's own implementation of this path is CUDA (no CPU rasterizer exists): "
+                                          "oracle/_ref/_refC.so = unmodified reference sources + GLM stand-in, timed on the same B200, "
+                                          "debug syncs off (the faster of the two ways the reference can run)"}
+    print(json.dumps(line))
+    if world > 1 and args.impl == "ours":
+        dist.barrier()
+    return 0
+
+
+def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, H, W, K, flush, refC, world, n_gpus, rank):
+    """The call a user makes: render(camera, model, pipe, bg) + loss.backward(), inputs from pinned host memory."""
+    import torch.distributed as dist
+    Npx = W * H
+    cam_host = [torch.cat([c.world_view_transform.flatten(), c.full_proj_transform.flatten(), c.camera_center.flatten()]).cpu().pin_memory()
+                for c in cams]
+    bg = torch.zeros(3, device=dev)
+    h2d = G_host.numel() * 4 + cam_host[0].numel() * 4
+    if args.impl == "ours":
+        from gaussian_renderer import render
+        pipe = SimpleNamespace(debug=False, convert_SHs_python=False, compute_cov3D_python=False)
+        pc = ModelView(scene, dev, None if quant is None else quant.to(dev), None if prune is None else prune.to(dev))
+
+        def one(i):
+            v = my_views[i % len(my_views)]
+            cm = cam_host[v].to(dev, non_blocking=True)
+            Gd = G_host.to(dev, non_blocking=True)
+            cam = SimpleNamespace(FoVx=cams[v].FoVx, FoVy=cams[v].FoVy, image_height=H, image_width=W,
+                                  world_view_transform=cm[:16].view(4, 4), full_proj_transform=cm[16:32].view(4, 4),
+                                  camera_center=cm[32:35])
+            for p in pc.params():
+                p.grad = None
+            pkg = render(cam, pc, pipe, bg)
+            loss = (pkg["render"] * Gd).sum()
+            loss.backward()
+            return float(loss.item())
+    else:
+        sd = scene.to(dev)
+        if prune is not None:
+            sd = sd.compact(~prune.to(dev).bool())
+
+        def one(i):
+            v = my_views[i % len(my_views)]
+            cm = cam_host[v].to(dev, non_blocking=True)
+            Gd = G_host.to(dev, non_blocking=True)
+            a = (bg, sd.means3D, EMPTY, sd.opacity, sd.scales, sd.rotations, 1.0, EMPTY, cm[:16].view(4, 4).contiguous(),
+                 cm[16:32].view(4, 4).contiguous(), tanx[v], tany[v], H, W, sd.sh, sd.degrees, cm[32:35].contiguous(), False, False)
+            R, color, radii, gb, bb, ib = refC.rasterize_gaussians(*a)
+            loss = (color * Gd).sum()
+            refC.rasterize_gaussians_backward(bg, sd.means3D, radii, EMPTY, sd.scales, sd.rotations, 1.0, EMPTY, a[8], a[9], a[10],
+                                              a[11], Gd, sd.sh, sd.degrees, a[16], gb, R, bb, ib, 0.0, False)
+            return float(loss.item())
+    for i in range(3):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1 and args.impl == "ours":
+        dist.barrier()
+    ms = 0.0
+    for i in range(K):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    if world > 1 and args.impl == "ours":
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": round(n_gpus * K * Npx / (ms * 1e-3) / 1e6, 2), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": 4, "ms_per_step": round(ms / K, 4),
+            "api": "gaussian_renderer.render + loss.backward()" if args.impl == "ours" else "_C.rasterize_gaussians + _C.rasterize_gaussians_backward"}
+
+
+def cpu_baseline(scene, prune, cam, W, H):
+    """Oracle (CPU port of the reference arithmetic) forward+backward on ONE view of the same workload, all host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gs_oracle
+    kw = dict(viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, campos=cam.camera_center, W=W, H=H,
+              tan_fovx=math.tan(cam.FoVx * 0.5), tan_fovy=math.tan(cam.FoVy * 0.5))
+    bg = np.zeros(3, np.float32)
+    dL = synth.grad_image(W, H, 1000).numpy()
+    t0 = time.time()
+    fwd = gs_oracle.forward(scene.means3D, scene.opacity, scene.scales, scene.rotations, scene.sh, scene.degrees, bg=bg,
+                            prune_mask=None if prune is None else prune.numpy(), **kw)
+    t1 = time.time()
+    if prune is None:
+        gs_oracle.backward(fwd, dL, scene.means3D, scene.scales, scene.rotations, scene.sh, scene.degrees, bg=bg, **kw)
+    t2 = time.time()
+    return {"value": round(W * H / (t2 - t0) / 1e6, 4), "unit": "Mpix/s", "cores": gs_oracle.num_threads(), "kind": "port",
+            "sample": f"1 view of the same workload, forward {t1 - t0:.2f} s + backward {t2 - t1:.2f} s (OpenMP, {os.cpu_count()} host CPUs)"}
+
+
+def reference_cpu_port(args, name, W, H, scene, cams, tanx, tany):
+    """--impl reference when oracle/_ref/_refC.so is not available: time the CPU oracle port instead."""
+    cpu = cpu_baseline(scene, None, cams[0].to("cpu"), W, H)
+    line = {"metric": "rendered Mpixels/s fwd+bwd", "value": cpu["value"], "unit": "Mpix/s", "n_gpus": 1, "steps": 1, "warmup": 0,
+            "ms_per_step": round(W * H / cpu["value"] / 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": f"{name}: {scene.P} Gaussians, {W}x{H}, fwd+bwd"},
+            "impl": "reference", "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

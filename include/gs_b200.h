@@ -156,6 +156,12 @@ GSB_API int gsb_export_image(const char* image_blob, int32_t width, int32_t heig
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 GSB_API uint64_t gsb_launch_count(void);
 
+/* Per-kernel device timing: when enabled, every kernel launch is bracketed by CUDA events on its stream;
+ * gsb_profile_read() waits for them, returns per-kernel totals since the previous read and resets.
+ * names[i] points to a static string. Returns the number of entries written. */
+GSB_API void gsb_profile_enable(int on);
+GSB_API int gsb_profile_read(int max_entries, const char** names, double* total_ms, uint64_t* launches);
+
 GSB_API const char* gsb_last_error(void);
 GSB_API const char* gsb_version(void);
 

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -19,6 +20,35 @@ void set_error(const char* fmt, ...)
 	vsnprintf(g_err, sizeof(g_err), fmt, ap);
 	va_end(ap);
 }
+
+// ---- per-kernel profiling --------------------------------------------------------------------
+static bool g_prof_on = false;
+struct ProfRec { int kid; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_cur = nullptr;
+static cudaEvent_t prof_event()
+{
+	if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+	cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int kid, cudaStream_t stream)
+{
+	(void)kid;
+	if (!g_prof_on) return;
+	g_prof_cur = prof_event();
+	cudaEventRecord(g_prof_cur, stream);
+}
+void prof_end(int kid, cudaStream_t stream)
+{
+	if (!g_prof_on || !g_prof_cur) return;
+	cudaEvent_t b = prof_event();
+	cudaEventRecord(b, stream);
+	g_prof_recs.push_back({ kid, g_prof_cur, b });
+	g_prof_cur = nullptr;
+}
+static const char* kKernelNames[K_COUNT] = { "preprocess", "scan", "emit_keys", "sort_hist", "sort_plan", "sort_pass", "tile_ranges",
+	"render_forward", "render_backward", "preprocess_backward", "mark_visible" };
 
 int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, int32_t*, const GsbDebug*, cudaStream_t);
 int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
@@ -69,6 +99,25 @@ size_t gsb_binning_bytes(int64_t R) { size_t b; BinningState::carve(nullptr, R, 
 uint64_t gsb_launch_count(void) { return g_launch_count; }
 const char* gsb_last_error(void) { return g_err; }
 const char* gsb_version(void) { return "gs_b200 0.1 (sm_100a)"; }
+
+void gsb_profile_enable(int on) { g_prof_on = on != 0; }
+
+int gsb_profile_read(int max_entries, const char** names, double* total_ms, uint64_t* launches)
+{
+	double ms[K_COUNT] = { 0 }; uint64_t n[K_COUNT] = { 0 };
+	for (auto& r : g_prof_recs)
+	{
+		cudaEventSynchronize(r.b);
+		float t = 0.f;
+		if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kid] += t; n[r.kid]++; }
+		g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+	}
+	g_prof_recs.clear();
+	int k = 0;
+	for (int i = 0; i < K_COUNT && k < max_entries; i++)
+		if (n[i]) { names[k] = kKernelNames[i]; total_ms[k] = ms[i]; launches[k] = n[i]; k++; }
+	return k;
+}
 
 int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_alloc, void* geom_user,
 	gsb_alloc_fn binning_alloc, void* binning_user, gsb_alloc_fn image_alloc, void* image_user,

@@ -280,6 +280,7 @@ int launch_preprocess_backward(const GsbScene* s, const GsbCamera* cam, const Ge
 	const int need = (s->P + 255) / 256;
 	const int grid = need < 148 * 8 ? need : 148 * 8;
 	const int smem = a.quant ? GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE * (int)sizeof(float) : 0;
+	ProfScope prof(K_PREPROCESS_BWD, stream);
 	if (a.quant) { if (grads->accumulate) preprocess_backward_kernel<true, true><<<grid, 256, smem, stream>>>(a); else preprocess_backward_kernel<true, false><<<grid, 256, smem, stream>>>(a); }
 	else { if (grads->accumulate) preprocess_backward_kernel<false, true><<<grid, 256, 0, stream>>>(a); else preprocess_backward_kernel<false, false><<<grid, 256, 0, stream>>>(a); }
 	GSB_LAUNCHED();

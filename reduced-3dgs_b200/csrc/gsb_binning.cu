@@ -359,6 +359,7 @@ static uint32_t higher_msb(uint32_t n)        // rasterizer_impl.cu:41-58 getHig
 int launch_scan(const GeomState& g, int P, cudaStream_t stream)
 {
 	const int blocks = (P + 256 * SCAN_ITEMS - 1) / (256 * SCAN_ITEMS);
+	ProfScope prof(K_SCAN, stream);
 	scan_kernel<<<blocks, 256, 0, stream>>>(g.tiles_touched, g.point_offsets, P, g.scan_state, g.counters);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
@@ -373,23 +374,28 @@ int launch_binning(const GeomState& g, const BinningState& b, char* bin_blob, co
 	sort_plan_init_kernel<<<1, 32, 0, stream>>>(b.plan);
 	GSB_LAUNCHED();
 	if (R == 0) { GSB_CUDA_OK(cudaGetLastError()); return GSB_OK; }
-	emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, g.tiles_touched, g.point_offsets, gx, b.keys[0], b.vals[0]);
+	{ ProfScope prof(K_EMIT_KEYS, stream);
+	emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, g.tiles_touched, g.point_offsets, gx, b.keys[0], b.vals[0]); }
 	GSB_LAUNCHED();
 	const int bits = 32 + (int)higher_msb((uint32_t)(gx * gy));                        // rasterizer_impl.cu:465-473
 	const int passes = (bits + 7) / 8;
 	const size_t n_tiles = BinningState::sort_tiles(R);
 	const int hist_blocks = (int)((n_tiles < 148 * 8) ? n_tiles : 148 * 8);
-	sort_hist_kernel<<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, b.hist);
+	{ ProfScope prof(K_SORT_HIST, stream);
+	sort_hist_kernel<<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, b.hist); }
 	GSB_LAUNCHED();
-	sort_plan_kernel<<<1, 256, 0, stream>>>(b.hist, R, passes, b.plan);
+	{ ProfScope prof(K_SORT_PLAN, stream);
+	sort_plan_kernel<<<1, 256, 0, stream>>>(b.hist, R, passes, b.plan); }
 	GSB_LAUNCHED();
 	for (int p = 0; p < passes; p++)
 	{
+		ProfScope prof(K_SORT_PASS, stream);
 		sort_pass_kernel<<<(unsigned)n_tiles, SORT_THREADS, 0, stream>>>(b.keys[0], b.keys[1], b.vals[0], b.vals[1], R, p, b.plan,
 			b.lookback, b.tickets, n_tiles);
 		GSB_LAUNCHED();
 	}
-	tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, b.keys[0], b.keys[1], b.plan, img.ranges);
+	{ ProfScope prof(K_TILE_RANGES, stream);
+	tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, b.keys[0], b.keys[1], b.plan, img.ranges); }
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
 	return GSB_OK;

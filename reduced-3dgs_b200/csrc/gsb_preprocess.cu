@@ -282,6 +282,7 @@ int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& 
 	if (dbg) a.dbg = *dbg;
 	a.prefiltered = cam->prefiltered;
 	const int blocks_needed = (s->P + 255) / 256;
+	ProfScope prof(K_PREPROCESS, stream);
 	if (a.quant)
 	{
 		const int smem = GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE * sizeof(float);
@@ -298,6 +299,7 @@ int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t stream)
 {
 	if (P <= 0) return GSB_OK;
+	ProfScope prof(K_MARK_VISIBLE, stream);
 	mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, view, present);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());

@@ -258,6 +258,7 @@ int launch_render_forward(const ImageState& img, const BinningState& b, const Ge
 	float* out_color, cudaStream_t stream)
 {
 	const dim3 grid((W + GSB_TILE_X - 1) / GSB_TILE_X, (H + GSB_TILE_Y - 1) / GSB_TILE_Y);
+	ProfScope prof(K_RENDER_FWD, stream);
 	render_forward_kernel<<<grid, 256, 0, stream>>>(img.ranges, b.vals[0], b.vals[1], b.plan, W, H, g.rec, bg,
 		img.final_T, img.n_contrib, out_color, img.tile_max_contrib);
 	GSB_LAUNCHED();
@@ -269,6 +270,7 @@ int launch_render_backward(const ImageState& img, const BinningState& b, const G
 	const float* dL_dpix, float* acc, cudaStream_t stream)
 {
 	const dim3 grid((W + GSB_TILE_X - 1) / GSB_TILE_X, (H + GSB_TILE_Y - 1) / GSB_TILE_Y);
+	ProfScope prof(K_RENDER_BWD, stream);
 	render_backward_kernel<<<grid, 256, 0, stream>>>(img.ranges, b.vals[0], b.vals[1], b.plan, W, H, g.rec, bg,
 		img.final_T, img.n_contrib, img.tile_max_contrib, dL_dpix, acc);
 	GSB_LAUNCHED();

@@ -98,13 +98,31 @@ def lib():
         L.gsb_export_binning.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsb_export_image.restype = C.c_int
         L.gsb_export_image.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsb_profile_enable.restype = None
+        L.gsb_profile_enable.argtypes = [C.c_int]
+        L.gsb_profile_read.restype = C.c_int
+        L.gsb_profile_read.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
 
+def profile_enable(on: bool):
+    lib().gsb_profile_enable(1 if on else 0)
+
+
+def profile_read() -> dict:
+    """{kernel name: (total ms, launches)} since the previous read (waits for the recorded events)."""
+    n = 16
+    names = (C.c_char_p * n)()
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint64 * n)()
+    k = lib().gsb_profile_read(n, names, ms, cnt)
+    return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(k)}
+
+
 EXPORTED_SYMBOLS = ["gsb_geom_bytes", "gsb_image_bytes", "gsb_binning_bytes", "gsb_forward", "gsb_backward",
                     "gsb_mark_visible", "gsb_export_binning", "gsb_export_image", "gsb_launch_count", "gsb_last_error",
-                    "gsb_version"]
+                    "gsb_version", "gsb_profile_enable", "gsb_profile_read"]
 
 
 def check(status: int):

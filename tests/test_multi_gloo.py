@@ -1,0 +1,80 @@
+"""CPU: the N>1 path (replicate scene / shard views / one gradient all-reduce) on world_size-2 gloo."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gs_b200 import multi
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert multi.world() == (rank, world)
+        views = multi.shard_views(7)
+        assert views == list(range(rank, 7, world))
+        # scene replication from rank 0
+        t = torch.arange(12, dtype=torch.float32).view(4, 3) if rank == 0 else torch.zeros(4, 3)
+        ids = torch.arange(8, dtype=torch.uint8) if rank == 0 else torch.zeros(8, dtype=torch.uint8)
+        multi.broadcast_scene([t, ids])
+        assert torch.equal(t, torch.arange(12, dtype=torch.float32).view(4, 3)) and torch.equal(ids, torch.arange(8, dtype=torch.uint8))
+        # per-view accumulation then ONE all-reduce; statistics are per view (non-linear), folded before the reduction
+        P, M = 5, 4
+        acc = multi.GradAccumulator(P, M, "cpu")
+        bufs = acc.buffers()
+        assert [tuple(b.shape) for b in bufs] == [(P, 3), (P, 3), (P, 1), (P, 3), (P, 6), (P, M, 3), (P, 3), (P, 4)]
+        for v in views:
+            g2d = torch.full((P, 3), float(v + 1))
+            radii = torch.tensor([v % 2, 1, 0, 2, 3 * (v + 1)])
+            for b in bufs:
+                b += (v + 1)
+            acc.observe_view(g2d, radii)
+        acc.all_reduce()
+        tot = sum(v + 1 for v in range(7))
+        for b in acc.buffers():
+            assert torch.all(b == tot)
+        assert float(acc.denom[1]) == 7 and float(acc.denom[2]) == 0
+        exp_norm = sum(math_sqrt2(v + 1) for v in range(7))
+        assert abs(float(acc.xyz_gradient_accum[1]) - exp_norm) < 1e-4
+        assert float(acc.max_radii2D[4]) == 21.0
+        imgs = multi.gather_images(torch.full((3, 2, 2), float(rank)))
+        if rank == 0:
+            assert [float(i.mean()) for i in imgs] == [0.0, 1.0]
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def math_sqrt2(x):
+    return (2 * x * x) ** 0.5
+
+
+def test_view_sharding_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_single_process_defaults():
+    assert multi.world() == (0, 1)
+    assert multi.shard_views(5) == [0, 1, 2, 3, 4]
+    acc = multi.GradAccumulator(3, 1, "cpu")
+    acc.all_reduce()
+    assert acc.flat.numel() == 3 * (3 + 3 + 1 + 3 + 6 + 3 + 3 + 4)
