@@ -153,6 +153,9 @@ GSB_API int gsb_export_binning(const char* binning_blob, int64_t num_rendered, u
 GSB_API int gsb_export_image(const char* image_blob, int32_t width, int32_t height, float* final_T, uint32_t* n_contrib,
                      uint32_t* ranges /* [tiles,2] */, void* stream);
 
+/* Test helper: the fused de-quantisation on its own -> activated scales [P,3], normalised rotations [P,4]. */
+GSB_API int gsb_debug_dequant(const GsbQuant* quant, int32_t P, float* scales, float* rotations, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 GSB_API uint64_t gsb_launch_count(void);
 

@@ -50,6 +50,7 @@ void prof_end(int kid, cudaStream_t stream)
 static const char* kKernelNames[K_COUNT] = { "preprocess", "scan", "emit_keys", "sort_hist", "sort_plan", "sort_pass", "tile_ranges",
 	"render_forward", "render_backward", "preprocess_backward", "mark_visible" };
 
+int launch_debug_dequant(const GsbQuant*, int, float*, float*, cudaStream_t);
 int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, int32_t*, const GsbDebug*, cudaStream_t);
 int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
 int launch_scan(const GeomState&, int, cudaStream_t);
@@ -189,6 +190,12 @@ int gsb_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, c
 	(void)projmatrix;
 	if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("mark_visible: bad arguments"); return GSB_EINVAL; }
 	return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+int gsb_debug_dequant(const GsbQuant* quant, int32_t P, float* scales, float* rotations, void* stream)
+{
+	if (!quant || !scales || !rotations) { set_error("gsb_debug_dequant: NULL argument"); return GSB_EINVAL; }
+	return launch_debug_dequant(quant, P, scales, rotations, (cudaStream_t)stream);
 }
 
 static __global__ void pick_sorted_kernel(const SortPlan* plan, const uint64_t* k0, const uint64_t* k1, const uint32_t* v0, const uint32_t* v1,

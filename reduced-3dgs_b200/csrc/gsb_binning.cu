@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, const float4* __r
 		{
 			off = offsets[idx] - t;
 			rc = rect[idx];
-			dbits = __float_as_uint(rec[3 * (size_t)idx + 2].y);
+			dbits = __float_as_uint(rec[3 * (size_t)idx + 2].z);
 		}
 	}
 	const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16, miny = rc.y & 0xffffu;

@@ -82,15 +82,6 @@ __device__ __forceinline__ void sh_to_rgb(int deg, float x, float y, float z, SH
 	}
 }
 
-// Quaternion normalisation of the de-quantised rotation = torch.nn.functional.normalize(q) (gaussian_model.py:145-146
-// get_rotation): q / max(||q||, 1e-12) with ||q|| = sqrt(fma chain over the 4 squares).
-__device__ __forceinline__ void normalize_quat(float& r, float& x, float& y, float& z)
-{
-	float n2 = __fmul_rn(r, r);
-	n2 = __fmaf_rn(x, x, n2); n2 = __fmaf_rn(y, y, n2); n2 = __fmaf_rn(z, z, n2);
-	const float n = fmaxf(__fsqrt_rn(n2), 1e-12f);
-	r = __fdiv_rn(r, n); x = __fdiv_rn(x, n); y = __fdiv_rn(y, n); z = __fdiv_rn(z, n);
-}
 
 template <bool QUANT>
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
@@ -220,11 +211,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 				radius_i = (int)my_radius;
 				tiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
 				rect = make_uint2(rmin.x | (rmax.x << 16), rmin.y | (rmax.y << 16));
-				const float pth = -__logf(255.0f * opacity);
+				const float pth = -__logf(255.0f * opacity) - 1e-3f;
 				float4* rec = a.g.rec + 3 * idx;
-				rec[0] = make_float4(conx, cony, conz, opacity);
-				rec[1] = make_float4(pix_x, pix_y, rgb[0], rgb[1]);
-				rec[2] = make_float4(rgb[2], tz, pth, 0.0f);
+				rec[0] = make_float4(conx, cony, conz, pth);
+				rec[1] = make_float4(pix_x, pix_y, opacity, rgb[0]);
+				rec[2] = make_float4(rgb[1], rgb[2], tz, 0.0f);
 				a.g.clamped[idx] = (uint8_t)clamp_bits;
 				visible = true;
 				if (a.dbg.depths) a.dbg.depths[idx] = tz;
@@ -250,6 +241,28 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= P) return;
 	present[idx] = xform_row(view, 2, means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]) > 0.2f;
+}
+
+// Debug/test export of the fused de-quantisation: activated scales [P,3] and normalised rotations [P,4] exactly as
+// preprocess_kernel<true> computes them (compared bit-for-bit with torch.exp / F.normalize in the tests).
+__global__ void debug_dequant_kernel(int P, GsbQuant q, float* __restrict__ scales, float* __restrict__ rots)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P) return;
+	const uint8_t* is = q.ids_scaling + 3 * (size_t)idx;
+	const uint8_t* ir = q.ids_rot + 4 * (size_t)idx;
+	for (int k = 0; k < 3; k++) scales[3 * (size_t)idx + k] = exp_ref(q.centers[17 * 256 + is[k]]);
+	float r = q.centers[18 * 256 + ir[0]], x = q.centers[19 * 256 + ir[1]], y = q.centers[19 * 256 + ir[2]], z = q.centers[19 * 256 + ir[3]];
+	normalize_quat(r, x, y, z);
+	reinterpret_cast<float4*>(rots)[idx] = make_float4(r, x, y, z);
+}
+
+int launch_debug_dequant(const GsbQuant* q, int P, float* scales, float* rots, cudaStream_t stream)
+{
+	if (P <= 0) return GSB_OK;
+	debug_dequant_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, *q, scales, rots);
+	GSB_CUDA_OK(cudaGetLastError());
+	return GSB_OK;
 }
 
 int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& g, int32_t* radii, const GsbDebug* dbg, cudaStream_t stream)

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 		{
 			const uint32_t id = point_list[b + tid];
 			const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
-			s_r0[tid] = r0; s_r1[tid] = r1; s_r2[tid] = make_float2(r2.x, r2.z);
+			s_r0[tid] = r0; s_r1[tid] = r1; s_r2[tid] = make_float2(r2.x, r2.y);
 		}
 		__syncthreads();
 		bool warp_done = __all_sync(0xffffffffu, done);
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 			if (j < n)
 			{
 				const float4 r0 = s_r0[j]; const float4 r1 = s_r1[j];
-				keep = rect_may_contribute(r1.x, r1.y, r0.x, r0.y, r0.z, s_r2[j].y, rx0, rx1, ry0, ry1);
+				keep = rect_may_contribute(r1.x, r1.y, r0.x, r0.y, r0.z, r0.w, rx0, rx1, ry0, ry1);
 			}
 			unsigned mask = __ballot_sync(0xffffffffu, keep);
 			while (mask)
@@ -75,14 +75,17 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 				const float4 r0 = s_r0[jj]; const float4 r1 = s_r1[jj];
 				const float dx = __fsub_rn(r1.x, pxf), dy = __fsub_rn(r1.y, pyf);
 				const float power = pair_power(r0.x, r0.y, r0.z, dx, dy);
-				if (power > 0.0f) continue;
-				const float alpha = fminf(0.99f, __fmul_rn(r0.w, exp_ref(power)));
+				// power > 0: reference `continue`; power < pth: alpha = opacity*exp(power) is provably < 1/255 (the
+				// reference's other `continue`), so the exp is skipped for most evaluated pairs
+				if (power > 0.0f || power < r0.w) continue;
+				const float alpha = fminf(0.99f, __fmul_rn(r1.z, exp_ref(power)));
 				if (alpha < 1.0f / 255.0f) continue;
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
 				if (test_T < 0.0001f) { done = true; continue; }
-				C0 = __fmaf_rn(T, __fmul_rn(r1.z, alpha), C0);
-				C1 = __fmaf_rn(T, __fmul_rn(r1.w, alpha), C1);
-				C2 = __fmaf_rn(T, __fmul_rn(s_r2[jj].x, alpha), C2);
+				const float2 gb = s_r2[jj];
+				C0 = __fmaf_rn(T, __fmul_rn(r1.w, alpha), C0);
+				C1 = __fmaf_rn(T, __fmul_rn(gb.x, alpha), C1);
+				C2 = __fmaf_rn(T, __fmul_rn(gb.y, alpha), C2);
 				T = test_T;
 				last = (b - range.x) + jj + 1;
 			}
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 		{
 			const uint32_t id = point_list[range.x + (hi - 1 - b - tid)];
 			const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
-			s_r0[tid] = r0; s_r1[tid] = r1; s_r2[tid] = make_float2(r2.x, r2.z); s_id[tid] = id;
+			s_r0[tid] = r0; s_r1[tid] = r1; s_r2[tid] = make_float2(r2.x, r2.y); s_id[tid] = id;
 		}
 #pragma unroll
 		for (int k = 0; k < ACC_STRIDE; k++) s_acc[k * 256 + tid] = 0.0f;   // plain zero fill of the [256][9] array
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 			if (j < n && (hi - 1 - b - j) < wmax)
 			{
 				const float4 r0 = s_r0[j]; const float4 r1 = s_r1[j];
-				keep = rect_may_contribute(r1.x, r1.y, r0.x, r0.y, r0.z, s_r2[j].y, rx0, rx1, ry0, ry1);
+				keep = rect_may_contribute(r1.x, r1.y, r0.x, r0.y, r0.z, r0.w, rx0, rx1, ry0, ry1);
 			}
 			unsigned mask = __ballot_sync(0xffffffffu, keep);
 			while (mask)
@@ -201,11 +204,11 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 				if (active)
 				{
 					const float power = pair_power(r0.x, r0.y, r0.z, dx, dy);
-					active = !(power > 0.0f);
+					active = !(power > 0.0f || power < r0.w);
 					if (active)
 					{
 						G = exp_ref(power);
-						alpha = fminf(0.99f, __fmul_rn(r0.w, G));
+						alpha = fminf(0.99f, __fmul_rn(r1.z, G));
 						active = !(alpha < 1.0f / 255.0f);
 					}
 				}
@@ -217,17 +220,18 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 					const float inv = __frcp_rn(one_m_alpha);
 					T = T * inv;                                                        // backward.cu:541
 					const float dchannel_dcolor = alpha * T;
-					const float cb = s_r2[jj].x;
+					const float2 gb = s_r2[jj];
+					const float cr = r1.w, cg = gb.x, cb = gb.y;
 					const float oml = 1.0f - last_alpha;
-					ar0 = last_alpha * lc0 + oml * ar0; lc0 = r1.z;
-					ar1 = last_alpha * lc1 + oml * ar1; lc1 = r1.w;
+					ar0 = last_alpha * lc0 + oml * ar0; lc0 = cr;
+					ar1 = last_alpha * lc1 + oml * ar1; lc1 = cg;
 					ar2 = last_alpha * lc2 + oml * ar2; lc2 = cb;
-					float dL_dalpha = (r1.z - ar0) * dLp0 + (r1.w - ar1) * dLp1 + (cb - ar2) * dLp2;
+					float dL_dalpha = (cr - ar0) * dLp0 + (cg - ar1) * dLp1 + (cb - ar2) * dLp2;
 					v0 = dchannel_dcolor * dLp0; v1 = dchannel_dcolor * dLp1; v2 = dchannel_dcolor * dLp2;
 					dL_dalpha *= T;
 					last_alpha = alpha;
 					dL_dalpha += (-T_final * inv) * bg_dot_dpixel;                      // backward.cu:569-572
-					const float dL_dG = r0.w * dL_dalpha;
+					const float dL_dG = r1.z * dL_dalpha;
 					const float gdx = G * dx, gdy = G * dy;
 					v3 = G * dL_dalpha;                                                 // dL_dopacity
 					v4 = dL_dG * (-gdx * r0.x - gdy * r0.y);                            // dL_dG * dG_ddelx

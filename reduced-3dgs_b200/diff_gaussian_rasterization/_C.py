@@ -197,3 +197,16 @@ def export_state(geomBuffer, binningBuffer, imageBuffer, R, W, H):
         _lib.check(L.gsb_export_image(ptr(imageBuffer), W, H, ptr(final_T), ptr(n_contrib), ptr(ranges), _lib.current_stream(device)))
     out.update(keys=keys, point_list=pl, final_T=final_T, n_contrib=n_contrib, ranges=ranges)
     return out
+
+
+def debug_dequant(quant):
+    """Fused de-quantisation on its own (test helper): -> (scales [P,3], rotations [P,4]) as the kernels compute them."""
+    device = quant.means3D.device
+    P = int(quant.means3D.shape[0])
+    keep = []
+    q = _quant_struct(quant, device, keep)
+    scales = torch.empty(P, 3, device=device)
+    rots = torch.empty(P, 4, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().gsb_debug_dequant(q, P, scales.data_ptr(), rots.data_ptr(), _lib.current_stream(device)))
+    return scales, rots

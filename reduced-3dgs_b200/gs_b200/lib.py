@@ -98,6 +98,8 @@ def lib():
         L.gsb_export_binning.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsb_export_image.restype = C.c_int
         L.gsb_export_image.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsb_debug_dequant.restype = C.c_int
+        L.gsb_debug_dequant.argtypes = [C.POINTER(GsbQuant), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsb_profile_enable.restype = None
         L.gsb_profile_enable.argtypes = [C.c_int]
         L.gsb_profile_read.restype = C.c_int
@@ -122,7 +124,7 @@ def profile_read() -> dict:
 
 EXPORTED_SYMBOLS = ["gsb_geom_bytes", "gsb_image_bytes", "gsb_binning_bytes", "gsb_forward", "gsb_backward",
                     "gsb_mark_visible", "gsb_export_binning", "gsb_export_image", "gsb_launch_count", "gsb_last_error",
-                    "gsb_version", "gsb_profile_enable", "gsb_profile_read"]
+                    "gsb_version", "gsb_profile_enable", "gsb_profile_read", "gsb_debug_dequant"]
 
 
 def check(status: int):
@@ -152,16 +154,25 @@ def f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
 
 class BlobAllocator:
     """Python side of gsb_alloc_fn: allocates a torch uint8 tensor (the reference's resizeFunctional,
-    rasterize_points.cu:33-41) and keeps it so it can be returned to the caller."""
+    rasterize_points.cu:33-41) and keeps it so it can be returned to the caller.
+    The ctypes callback closes over a plain list, NOT over `self`: a bound-method callback would form a reference
+    cycle (self -> cb -> self) and keep the blobs alive until the cyclic GC runs, defeating the caching allocator."""
 
     def __init__(self, device):
-        self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = ALLOC_FN(self._alloc)
+        holder = []
 
-    def _alloc(self, _user, nbytes):
-        self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self.tensor.data_ptr()
+        def alloc(_user, nbytes, _holder=holder, _device=device):
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=_device)
+            _holder.append(t)
+            return t.data_ptr()
+
+        self._holder = holder
+        self.cb = ALLOC_FN(alloc)
+        self._empty = torch.empty(0, dtype=torch.uint8, device=device)
+
+    @property
+    def tensor(self):
+        return self._holder[-1] if self._holder else self._empty
 
 
 def current_stream(device) -> int:
