@@ -63,36 +63,49 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (pynvml) from a thread.
+    (Polling with the nvidia-smi binary perturbs the run: each query stalls kernel launches for milliseconds.)"""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_sm = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self._thread.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 def physical_gpu_index(local: int) -> int:
@@ -183,7 +196,7 @@ def main():
     dev = torch.device("cuda", local)
     name, W, H, scene, quant, prune = build_workload(args, dev, rank, world)
     Npx = W * H
-    cams = [c.to(dev) for c in bench_cameras(W, H)]
+    cams = [c.to(dev) for c in bench_cameras(W, H, 4 * world)]
     my_views = list(range(rank, len(cams), world)) if args.impl == "ours" else list(range(len(cams)))
     bg = torch.zeros(3, device=dev)
     G_host = synth.grad_image(W, H, 1000 + rank).pin_memory()
@@ -245,7 +258,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident measurement (`value`) ----------------
-    for i in range(max(Wm, 3)):
+    for i in range(max(Wm, 4)):          # every distinct view of this rank at least once (allocator warm-up)
         out = step(i, G)
     R0, color0, radii0, ib0, _ = out
     torch.cuda.synchronize()
@@ -314,7 +327,7 @@ def main():
         rho = float(tile_max.sum().item()) / max(R0, 1)
         Nt = ((W + 15) // 16) * ((H + 15) // 16)
         B = algorithmic_bytes(sd.P, V, R0, sumK, Npx, Nt, rho, rho, quant is not None, prune is not None)
-        groups = {"preprocess": ["preprocess"], "binning": ["scan", "emit_keys", "sort_hist", "sort_plan", "sort_pass", "tile_ranges"],
+        groups = {"preprocess": ["preprocess"], "binning": ["tile_scan", "scatter", "tile_sort", "tile_sort_large"],
                   "render_forward": ["render_forward"], "render_backward": ["render_backward"], "preprocess_backward": ["preprocess_backward"]}
         per_kernel = {k: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K} for k, v in prof.items()}
         stage_ms = {g: sum(prof.get(k, (0, 0))[0] for k in ks) / K for g, ks in groups.items()}
@@ -337,7 +350,7 @@ def main():
         cpu = cpu_baseline(scene, prune, cams[0].to("cpu"), W, H)
 
     line = {"metric": "rendered Mpixels/s fwd+bwd", "value": round(value, 2), "unit": "Mpix/s", "n_gpus": n_gpus, "steps": K,
-            "warmup": max(Wm, 3), "ms_per_step": round(total_ms / K, 4), "higher_is_better": True, "scaling": "weak",
+            "warmup": max(Wm, 4), "ms_per_step": round(total_ms / K, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{name}: {scene.P} Gaussians, {W}x{H}, fwd+bwd, one view per step"
                                    + (", codebook-quantised (fused dequant)" if (quant is not None and args.impl == 'ours') else "")
@@ -346,7 +359,8 @@ def main():
                        "l2": "256 MB flush write between steps (outside the per-step event pairs)",
                        "parallelism": f"views sharded over {n_gpus} GPU(s), scene replicated"
                                       + (", one gradient all-reduce per K-view batch" if n_gpus > 1 else "")},
-            "impl": args.impl, "clocks": clocks}
+            "impl": args.impl, "clocks": clocks,
+            "step_ms": {"min": round(min(step_ms), 4), "median": round(float(np.median(step_ms)), 4), "max": round(max(step_ms), 4)}}
     if e2e is not None:
         line["e2e"] = e2e
     if launches is not None:

@@ -148,8 +148,9 @@ GSB_API int gsb_mark_visible(int32_t P, const float* means3D, const float* viewm
                      uint8_t* present, void* stream);
 
 /* Decode pieces of the private blobs (test / tooling helpers; layouts are private and may change). */
-GSB_API int gsb_export_binning(const char* binning_blob, int64_t num_rendered, uint64_t* keys_sorted, uint32_t* point_list,
-                       void* stream);
+GSB_API int gsb_export_binning(const char* geom_blob, int32_t P, const char* binning_blob, int64_t num_rendered,
+                       const char* image_blob, int32_t width, int32_t height,
+                       uint64_t* keys_sorted /* tile << 32 | depth bits */, uint32_t* point_list, void* stream);
 GSB_API int gsb_export_image(const char* image_blob, int32_t width, int32_t height, float* final_T, uint32_t* n_contrib,
                      uint32_t* ranges /* [tiles,2] */, void* stream);
 

@@ -47,14 +47,15 @@ void prof_end(int kid, cudaStream_t stream)
 	g_prof_recs.push_back({ kid, g_prof_cur, b });
 	g_prof_cur = nullptr;
 }
-static const char* kKernelNames[K_COUNT] = { "preprocess", "scan", "emit_keys", "sort_hist", "sort_plan", "sort_pass", "tile_ranges",
+static const char* kKernelNames[K_COUNT] = { "preprocess", "tile_scan", "scatter", "tile_sort_large", "unused4", "tile_sort", "unused6",
 	"render_forward", "render_backward", "preprocess_backward", "mark_visible" };
 
 int launch_debug_dequant(const GsbQuant*, int, float*, float*, cudaStream_t);
-int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, int32_t*, const GsbDebug*, cudaStream_t);
+int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, uint32_t*, int32_t*, const GsbDebug*, cudaStream_t);
 int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
-int launch_scan(const GeomState&, int, cudaStream_t);
-int launch_binning(const GeomState&, const BinningState&, char*, const ImageState&, int, long long, int, int, cudaStream_t);
+int launch_tile_scan(const ImageState&, const GeomState&, int, int, cudaStream_t);
+int launch_binning(const GeomState&, const BinningState&, const ImageState&, int, long long, int, int, cudaStream_t);
+int launch_export_binning(const GeomState&, const BinningState&, const ImageState&, int, int, uint64_t*, uint32_t*, cudaStream_t);
 int launch_render_forward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, float*, cudaStream_t);
 int launch_render_backward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, const float*, float*, cudaStream_t);
 int launch_preprocess_backward(const GsbScene*, const GsbCamera*, const GeomState&, const int32_t*, const float*, const GsbGrads*, float, cudaStream_t);
@@ -101,7 +102,12 @@ uint64_t gsb_launch_count(void) { return g_launch_count; }
 const char* gsb_last_error(void) { return g_err; }
 const char* gsb_version(void) { return "gs_b200 0.1 (sm_100a)"; }
 
-void gsb_profile_enable(int on) { g_prof_on = on != 0; }
+void gsb_profile_enable(int on)
+{
+	g_prof_on = on != 0;
+	// cudaEventCreate costs tens of microseconds: create the pool up front so the timed region only records
+	if (g_prof_on) while (g_prof_pool.size() < 4096) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; g_prof_pool.push_back(e); }
+}
 
 int gsb_profile_read(int max_entries, const char** names, double* total_ms, uint64_t* launches)
 {
@@ -141,10 +147,10 @@ int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_a
 	if (!geom_blob || !img_blob) { set_error("scratch allocation failed"); return GSB_ENOMEM; }
 	GeomState g = GeomState::carve(geom_blob, P);
 	ImageState img = ImageState::carve(img_blob, W, H);
-	GSB_CUDA_OK(cudaMemsetAsync(g.scan_state, 0, GeomState::scan_blocks(P) * sizeof(unsigned long long), stream));
 	GSB_CUDA_OK(cudaMemsetAsync(g.counters, 0, 16 * sizeof(uint32_t), stream));
-	if (int e = launch_preprocess(scene, cam, g, radii, debug, stream)) return e;
-	if (int e = launch_scan(g, P, stream)) return e;
+	GSB_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, ImageState::tiles(W, H) * sizeof(uint32_t), stream));
+	if (int e = launch_preprocess(scene, cam, g, img.tile_count, radii, debug, stream)) return e;
+	if (int e = launch_tile_scan(img, g, W, H, stream)) return e;
 	// the instance count sizes the binning blob (rasterizer_impl.cu:445-450): one 16-byte read-back
 	static thread_local uint32_t* h_counters = nullptr;
 	if (!h_counters) GSB_CUDA_OK(cudaMallocHost(&h_counters, 16 * sizeof(uint32_t)));
@@ -152,12 +158,12 @@ int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_a
 	GSB_CUDA_OK(cudaStreamSynchronize(stream));
 	const long long R = h_counters[0];
 	if (h_counters[3]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSB_ECUDA; }
-	if (R >= (1ll << 30)) { set_error("%lld (Gaussian, tile) instances exceed the 2^30 limit of the sorter", R); return GSB_ERANGE; }
+	if (R >= (1ll << 31)) { set_error("%lld (Gaussian, tile) instances do not fit 31 bits", R); return GSB_ERANGE; }
 	*num_rendered = R;
 	char* bin_blob = binning_alloc(binning_user, gsb_binning_bytes(R));
 	if (!bin_blob) { set_error("binning allocation failed"); return GSB_ENOMEM; }
 	BinningState b = BinningState::carve(bin_blob, R);
-	if (int e = launch_binning(g, b, bin_blob, img, P, R, W, H, stream)) return e;
+	if (int e = launch_binning(g, b, img, P, R, W, H, stream)) return e;
 	if (int e = launch_render_forward(img, b, g, W, H, cam->background, out_color, stream)) return e;
 	return GSB_OK;
 }
@@ -198,23 +204,14 @@ int gsb_debug_dequant(const GsbQuant* quant, int32_t P, float* scales, float* ro
 	return launch_debug_dequant(quant, P, scales, rotations, (cudaStream_t)stream);
 }
 
-static __global__ void pick_sorted_kernel(const SortPlan* plan, const uint64_t* k0, const uint64_t* k1, const uint32_t* v0, const uint32_t* v1,
-	long long R, uint64_t* keys, uint32_t* vals)
-{
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= R) return;
-	const bool f = plan->final_buf != 0;
-	if (keys) keys[i] = f ? k1[i] : k0[i];
-	if (vals) vals[i] = f ? v1[i] : v0[i];
-}
-
-int gsb_export_binning(const char* binning_blob, int64_t R, uint64_t* keys_sorted, uint32_t* point_list, void* stream)
+int gsb_export_binning(const char* geom_blob, int32_t P, const char* binning_blob, int64_t R, const char* image_blob, int32_t W, int32_t H,
+	uint64_t* keys_sorted, uint32_t* point_list, void* stream)
 {
 	if (R <= 0) return GSB_OK;
+	GeomState g = GeomState::carve(const_cast<char*>(geom_blob), P);
 	BinningState b = BinningState::carve(const_cast<char*>(binning_blob), R);
-	pick_sorted_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(b.plan, b.keys[0], b.keys[1], b.vals[0], b.vals[1], R, keys_sorted, point_list);
-	GSB_CUDA_OK(cudaGetLastError());
-	return GSB_OK;
+	ImageState img = ImageState::carve(const_cast<char*>(image_blob), W, H);
+	return launch_export_binning(g, b, img, W, H, keys_sorted, point_list, (cudaStream_t)stream);
 }
 
 int gsb_export_image(const char* image_blob, int32_t W, int32_t H, float* final_T, uint32_t* n_contrib, uint32_t* ranges, void* stream_)

@@ -73,7 +73,22 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 		const bool valid = lane < n_valid;
 		const bool vis = valid && a.radii[idx] > 0;
 		// ---- stage the warp's SH rows -------------------------------------------------------------
-		if (have_sh && !QUANT)
+		if (have_sh && !QUANT && RL == 48 && n_valid == 32)
+		{
+			// M == 16 fast path: 12 independent 128-bit loads per lane (6 KB contiguous per warp), then scatter to padded rows
+			const float4* src4 = reinterpret_cast<const float4*>(a.shs + base * 48);
+			float4 v[12];
+#pragma unroll
+			for (int i = 0; i < 12; i++) v[i] = src4[i * 32 + lane];
+#pragma unroll
+			for (int i = 0; i < 12; i++)
+			{
+				const int f = (i * 32 + lane) * 4, row = f / 48, col = f - row * 48;
+				float* d = s_row + row * RS + col;
+				d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+			}
+		}
+		else if (have_sh && !QUANT)
 		{
 			const float* src = a.shs + base * RL;
 			int row = 0, col = lane;
@@ -290,7 +305,20 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 		}
 		__syncwarp();
 		// ---- unit-stride write-back ------------------------------------------------------------------
-		if (a.out.dL_dsh)
+		if (a.out.dL_dsh && RL == 48 && n_valid == 32)
+		{
+			float4* dst4 = reinterpret_cast<float4*>(a.out.dL_dsh + base * 48);
+#pragma unroll
+			for (int i = 0; i < 12; i++)
+			{
+				const int f = (i * 32 + lane) * 4, row = f / 48, col = f - row * 48;
+				const float* sp = s_row + row * RS + col;
+				float4 o = have_sh ? make_float4(sp[0], sp[1], sp[2], sp[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+				if (ACC) { const float4 c = dst4[i * 32 + lane]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+				dst4[i * 32 + lane] = o;
+			}
+		}
+		else if (a.out.dL_dsh)
 		{
 			float* dst = a.out.dL_dsh + base * RL;
 			int row = 0, col = lane;

@@ -1,402 +1,361 @@
-// gsb_binning.cu — tile binning: prefix sum, key emission, stable LSD radix sort, tile ranges (sm_100a).
+// gsb_binning.cu — tile binning for sm_100a: count -> scan -> scatter -> per-tile sort.
 //
-// Replaces, with hand-written kernels (no CUB):
-//   cub::DeviceScan::InclusiveSum           rasterizer_impl.cu:441   -> scan_kernel (single pass, decoupled look-back)
-//   duplicateWithKeys                       rasterizer_impl.cu:78-119 -> emit_keys_kernel
-//   cub::DeviceRadixSort::SortPairs         rasterizer_impl.cu:468   -> sort_hist / sort_plan / sort_pass (onesweep:
-//                                            one histogram sweep, then one read+write sweep per 8-bit digit;
-//                                            digits in which every key agrees are skipped on the device)
-//   cudaMemset + identifyTileRanges         rasterizer_impl.cu:475-482 -> tile_ranges_kernel
-// All of it is integer work and bit-exact by construction: keys are (tile << 32 | depth bits), the sort is
-// stable, so ties keep emission order (ascending Gaussian index).
+// What the reference does (rasterizer_impl.cu:441-482): inclusive scan of tiles_touched, duplicateWithKeys into
+// R (tile << 32 | depth bits, gaussian id) pairs, ONE global cub::DeviceRadixSort over all R 64-bit keys
+// (6 digit passes = ~150 B of HBM traffic per instance), then identifyTileRanges.
+//
+// What this file does instead — same result, bit for bit, ~20 B per instance:
+//   1. the preprocess kernel already counted the instances of every tile (one RED per (Gaussian, tile));
+//   2. tile_scan_kernel: exclusive scan of the T tile counters -> ranges[t] = (start, end) directly
+//      (== identifyTileRanges' output) and R;
+//   3. scatter_kernel: every (Gaussian, tile) instance claims a slot in its tile's segment with an atomic cursor and
+//      stores the 64-bit composite (depth bits << 32 | gaussian id);
+//   4. tile_sort_kernel: one CTA per tile sorts its segment entirely in shared memory: a stable 8-bit LSD radix sort on the
+//      32 depth bits (digits in which all keys of the tile agree are skipped), then the (rare) runs of bit-identical depths
+//      are put in ascending Gaussian id, and the ids are written -> point_list.
+// The global stable sort by (tile, depth) with ties in emission order (ascending Gaussian id) is exactly "per tile, sort
+// by (depth bits, id)": a Gaussian appears at most once per tile, so the composites are unique and the order is total.
+// Segments larger than the shared-memory classes (> 8192 instances in one tile) fall back to a single-CTA global-memory
+// LSD radix sort on the 64-bit composite.
+// (The first version of this file was a hand-written 8-bit onesweep radix sort; see git history and DESIGN.md.)
 #include "gsb_common.cuh"
 
 namespace gsb {
 
 // ------------------------------------------------------------------------------------------------
-// Inclusive scan of tiles_touched, 2048 items per block, chained through 64-bit look-back cells
-// (flag << 32 | value; flag 1 = block aggregate, 2 = inclusive prefix).  Block order = ticket order.
-#define SCAN_ITEMS 8
-__global__ void __launch_bounds__(256) scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
-	unsigned long long* state, uint32_t* counters)
+// Exclusive scan over the tile counters (T <= a few 10^4): one CTA, 1024 threads, sequential chunks.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ tile_count, int T, uint2* __restrict__ ranges,
+	uint32_t* __restrict__ counters, uint32_t* __restrict__ cursor, uint32_t* __restrict__ cls_list, uint32_t* __restrict__ cls_count)
 {
-	__shared__ uint32_t s_warp[8];
-	__shared__ uint32_t s_block, s_prefix;
-	if (threadIdx.x == 0) s_block = atomicAdd(&counters[2], 1u);
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_carry;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) { s_carry = 0; cls_count[0] = 0; cls_count[1] = 0; }
 	__syncthreads();
-	const uint32_t bid = s_block;
-	const long long base = (long long)bid * (256 * SCAN_ITEMS) + threadIdx.x * SCAN_ITEMS;
-	uint32_t v[SCAN_ITEMS];
-	uint32_t sum = 0;
-	if (base + SCAN_ITEMS <= n)
+	for (int base = 0; base < T; base += 1024)
 	{
-		const uint4 a = reinterpret_cast<const uint4*>(in + base)[0], b = reinterpret_cast<const uint4*>(in + base)[1];
-		v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-	}
-	else
-	{
+		const int t = base + tid;
+		const uint32_t c = t < T ? tile_count[t] : 0u;
+		uint32_t incl = c;
 #pragma unroll
-		for (int i = 0; i < SCAN_ITEMS; i++) v[i] = (base + i < n) ? in[base + i] : 0u;
-	}
-#pragma unroll
-	for (int i = 0; i < SCAN_ITEMS; i++) { sum += v[i]; v[i] = sum; }
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t incl = sum;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-	if (lane == 31) s_warp[warp] = incl;
-	__syncthreads();
-	uint32_t warp_excl = 0, block_total = 0;
-#pragma unroll
-	for (int w = 0; w < 8; w++) { const uint32_t t = s_warp[w]; if (w < warp) warp_excl += t; block_total += t; }
-	if (threadIdx.x == 0)
-	{
-		uint32_t prefix = 0;
-		if (bid > 0)
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+		if (lane == 31) s_warp[warp] = incl;
+		__syncthreads();
+		if (warp == 0)
 		{
-			atomicExch(&state[bid], (1ull << 32) | block_total);
-			long long j = (long long)bid - 1;
-			while (true)
-			{
-				unsigned long long c;
-				do { c = *reinterpret_cast<volatile unsigned long long*>(&state[j]); } while ((c >> 32) == 0);
-				prefix += (uint32_t)c;
-				if ((c >> 32) == 2) break;
-				j--;
-			}
-		}
-		__threadfence();
-		atomicExch(&state[bid], (2ull << 32) | (uint32_t)(prefix + block_total));
-		s_prefix = prefix;
-		if ((long long)(bid + 1) * (256 * SCAN_ITEMS) >= n) counters[0] = prefix + block_total;   // num_rendered
-	}
-	__syncthreads();
-	const uint32_t off = s_prefix + warp_excl + (incl - sum);
-	if (base + SCAN_ITEMS <= n)
-	{
-		reinterpret_cast<uint4*>(out + base)[0] = make_uint4(v[0] + off, v[1] + off, v[2] + off, v[3] + off);
-		reinterpret_cast<uint4*>(out + base)[1] = make_uint4(v[4] + off, v[5] + off, v[6] + off, v[7] + off);
-	}
-	else
-	{
+			uint32_t w = s_warp[lane];
 #pragma unroll
-		for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) out[base + i] = v[i] + off;
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+			s_warp[lane] = w;
+		}
+		__syncthreads();
+		const uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
+		if (t < T)
+		{
+			ranges[t] = make_uint2(start, start + c); cursor[t] = 0;
+			// tiles too large for the one-CTA-per-tile class are queued for the persistent large-segment kernels
+			if (c > GSB_SORT_CAP_A) { const int k = c > GSB_SORT_CAP_B; cls_list[k * T + atomicAdd(&cls_count[k], 1u)] = t; }
+		}
+		__syncthreads();
+		if (tid == 1023) s_carry = start + c;
+		__syncthreads();
 	}
+	if (tid == 0) counters[0] = s_carry;            // num_rendered
 }
 
 // ------------------------------------------------------------------------------------------------
-// duplicateWithKeys: one warp per 32 Gaussians; a Gaussian's tiles are written by the whole warp when it
-// covers many tiles (no single-thread serial loop over a large splat), otherwise by its own lane.
-__global__ void __launch_bounds__(256) emit_keys_kernel(int P, const float4* __restrict__ rec, const uint2* __restrict__ rect,
-	const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets, int gx,
-	uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+// One thread per Gaussian writes its instances; Gaussians covering more than 32 tiles are handled by the whole warp.
+__global__ void __launch_bounds__(256) scatter_kernel(int P, const float4* __restrict__ rec, const uint2* __restrict__ rect,
+	const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, int gx, uint64_t* __restrict__ bucket)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
-	uint32_t t = 0, off = 0, dbits = 0; uint2 rc = make_uint2(0, 0);
+	uint2 rc = make_uint2(0, 0); uint32_t dbits = 0;
 	if (idx < P)
 	{
-		t = tiles_touched[idx];
-		if (t)
-		{
-			off = offsets[idx] - t;
-			rc = rect[idx];
-			dbits = __float_as_uint(rec[3 * (size_t)idx + 2].z);
-		}
+		rc = rect[idx];
+		if (rc.x | rc.y) dbits = __float_as_uint(rec[3 * (size_t)idx + 2].z);
 	}
-	const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16, miny = rc.y & 0xffffu;
-	const uint32_t w = maxx - minx;
-	const bool big = t > 16;
+	const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16, miny = rc.y & 0xffffu, maxy = rc.y >> 16;
+	const uint32_t w = maxx - minx, t = w * (maxy - miny);
+	const bool big = t > 32;
 	if (t && !big)
 	{
-		uint32_t x = minx, y = miny;
-		for (uint32_t k = 0; k < t; k++)
-		{
-			keys[off + k] = ((uint64_t)(y * gx + x) << 32) | dbits;
-			vals[off + k] = (uint32_t)idx;
-			if (++x == maxx) { x = minx; y++; }
-		}
+		const uint64_t comp = ((uint64_t)dbits << 32) | (uint32_t)idx;
+		for (uint32_t y = miny; y < maxy; y++)
+			for (uint32_t x = minx; x < maxx; x++)
+			{
+				const uint32_t tile = y * gx + x;
+				bucket[ranges[tile].x + atomicAdd(&cursor[tile], 1u)] = comp;
+			}
 	}
 	unsigned bigmask = __ballot_sync(0xffffffffu, big);
 	while (bigmask)
 	{
 		const int src = __ffs(bigmask) - 1; bigmask &= bigmask - 1;
-		const uint32_t bt = __shfl_sync(0xffffffffu, t, src), boff = __shfl_sync(0xffffffffu, off, src);
+		const uint32_t bt = __shfl_sync(0xffffffffu, t, src), bw = __shfl_sync(0xffffffffu, w, src);
 		const uint32_t bminx = __shfl_sync(0xffffffffu, minx, src), bminy = __shfl_sync(0xffffffffu, miny, src);
-		const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bd = __shfl_sync(0xffffffffu, dbits, src);
-		const uint32_t bidx = (uint32_t)(idx - lane + src);
+		const uint64_t comp = ((uint64_t)__shfl_sync(0xffffffffu, dbits, src) << 32) | (uint32_t)(idx - lane + src);
 		for (uint32_t k = lane; k < bt; k += 32)
 		{
-			const uint32_t y = bminy + k / bw, x = bminx + k % bw;
-			keys[boff + k] = ((uint64_t)(y * gx + x) << 32) | bd;
-			vals[boff + k] = bidx;
+			const uint32_t tile = (bminy + k / bw) * gx + bminx + k % bw;
+			bucket[ranges[tile].x + atomicAdd(&cursor[tile], 1u)] = comp;
 		}
 	}
 }
 
 // ------------------------------------------------------------------------------------------------
-// Radix sort, 8-bit digits.
-__global__ void __launch_bounds__(256) sort_hist_kernel(const uint64_t* __restrict__ keys, long long R, int passes, uint32_t* __restrict__ hist)
+// Per-tile sort in shared memory: stable LSD radix sort of (depth bits, id) pairs on the 32 depth bits, 8 bits per pass.
+// Warp w owns positions [w*32*ITEMS, (w+1)*32*ITEMS); ranks inside a warp come from match.any, across warps from a
+// per-digit scan of the per-warp counters (the same stable ranking as a onesweep tile, but the whole "array" is the tile).
+// LIST == false: one CTA per tile (blockIdx.x = tile), tiles with more than CAP instances are skipped (they are on a list).
+// LIST == true : persistent CTAs walk the queued tile list.
+template <int CAP, int THREADS, bool LIST>
+__global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
+	uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cls_list, const uint32_t* __restrict__ cls_count)
 {
-	__shared__ uint32_t s_h[GSB_SORT_MAX_PASSES * 256];
-	for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) s_h[i] = 0;
-	__syncthreads();
-	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x)
-	{
-		const uint64_t k = keys[i];
-		for (int p = 0; p < passes; p++) atomicAdd(&s_h[p * 256 + (uint32_t)((k >> (8 * p)) & 0xff)], 1u);
-	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) { const uint32_t c = s_h[i]; if (c) atomicAdd(&hist[i], c); }
-}
-
-// One block: exclusive digit offsets per pass, skip flags (all keys share the digit) and ping-pong schedule.
-__global__ void __launch_bounds__(256) sort_plan_kernel(const uint32_t* __restrict__ hist, long long R, int passes, SortPlan* plan)
-{
-	__shared__ uint32_t s_scan[256];
-	__shared__ uint32_t s_skip[GSB_SORT_MAX_PASSES];
-	const int d = threadIdx.x;
-	if (d < GSB_SORT_MAX_PASSES) s_skip[d] = 0;
-	__syncthreads();
-	for (int p = 0; p < passes; p++)
-	{
-		const uint32_t c = hist[p * 256 + d];
-		if (c == (uint32_t)R) s_skip[p] = 1;           // at most one thread per pass can see this
-		if (d == 0 && R == 0) s_skip[p] = 1;
-		s_scan[d] = c;
-		__syncthreads();
-		for (int o = 1; o < 256; o <<= 1)
-		{
-			const uint32_t t = d >= o ? s_scan[d - o] : 0u;
-			__syncthreads();
-			s_scan[d] += t;
-			__syncthreads();
-		}
-		plan->digit_base[p][d] = s_scan[d] - c;
-		__syncthreads();
-	}
-	if (d == 0)
-	{
-		uint32_t cur = 0;
-		for (int p = 0; p < passes; p++)
-		{
-			const uint32_t sk = s_skip[p] == 1;
-			plan->skip[p] = sk; plan->src[p] = cur;
-			if (!sk) cur ^= 1u;
-		}
-		plan->final_buf = cur;
-	}
-}
-
-__global__ void sort_plan_init_kernel(SortPlan* plan)
-{
-	if (threadIdx.x < GSB_SORT_MAX_PASSES) { plan->skip[threadIdx.x] = 0; plan->src[threadIdx.x] = 0; }
-	if (threadIdx.x == 0) plan->final_buf = 0;
-}
-
-// One onesweep pass.  Tile = 4096 consecutive keys handled by 256 threads; warp w ranks keys
-// [w*512, (w+1)*512) in 16 warp-wide steps with match.any (stable), then digit counts are chained across tiles.
-#define SORT_THREADS 256
-#define SORT_ITEMS 16
-#define LB_AGG 0x40000000u
-#define LB_INC 0x80000000u
-#define LB_VAL 0x3fffffffu
-__global__ void __launch_bounds__(SORT_THREADS) sort_pass_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1,
-	long long R, int pass, const SortPlan* __restrict__ plan, uint32_t* lookback_all, uint32_t* tickets, size_t n_tiles)
-{
-	if (plan->skip[pass]) return;
-	const uint32_t srcb = plan->src[pass];
-	const uint64_t* __restrict__ kin = srcb ? keys1 : keys0;
-	uint64_t* __restrict__ kout = srcb ? keys0 : keys1;
-	const uint32_t* __restrict__ vin = srcb ? vals1 : vals0;
-	uint32_t* __restrict__ vout = srcb ? vals0 : vals1;
-	uint32_t* lookback = lookback_all + (size_t)pass * n_tiles * 256;
-
-	__shared__ uint32_t s_whist[8][256];           // per-warp digit counts, later per-warp exclusive offsets
-	__shared__ uint32_t s_dstart[256];             // tile-local start of each digit run
-	__shared__ uint32_t s_gbase[256];              // global start of this tile's run of each digit
-	__shared__ uint64_t s_keys[GSB_SORT_TILE];
-	__shared__ uint32_t s_tile;
-	uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys);   // reused after the key write-out
-
+	constexpr int ITEMS = CAP / THREADS, NW = THREADS / 32;
+	extern __shared__ __align__(16) unsigned char s_raw[];
+	uint32_t* kA = reinterpret_cast<uint32_t*>(s_raw);
+	uint32_t* vA = kA + CAP;
+	uint32_t* kB = vA + CAP;
+	uint32_t* vB = kB + CAP;
+	uint32_t* whist = vB + CAP;                 // [NW][256]
+	__shared__ uint32_t s_dstart[256];
+	__shared__ uint32_t s_wtot[8];
+	__shared__ uint32_t s_and, s_or;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) s_tile = atomicAdd(&tickets[pass], 1u);
-	for (int i = tid; i < 8 * 256; i += SORT_THREADS) (&s_whist[0][0])[i] = 0;
-	__syncthreads();
-	const uint32_t tile = s_tile;
-	const long long tbase = (long long)tile * GSB_SORT_TILE;
-	const int count = (int)min((long long)GSB_SORT_TILE, R - tbase);
-	const int shift = 8 * pass;
-
-	uint64_t key[SORT_ITEMS];
-	uint32_t rank[SORT_ITEMS];
 	const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++)
+	const uint32_t n_work = LIST ? *cls_count : gridDim.x;
+	for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x)
 	{
-		const int local = warp * (32 * SORT_ITEMS) + i * 32 + lane;
-		const bool valid = local < count;
-		key[i] = valid ? kin[tbase + local] : ~0ull;
-		const uint32_t d = valid ? (uint32_t)((key[i] >> shift) & 0xff) : 256u;
-		const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-		unsigned m = __match_any_sync(0xffffffffu, d) & vmask;
-		if (valid)
-		{
-			const int leader = __ffs(m) - 1;
-			uint32_t old = 0;
-			if (lane == leader) { old = s_whist[warp][d]; s_whist[warp][d] = old + __popc(m); }
-			old = __shfl_sync(m, old, leader);
-			rank[i] = old + __popc(m & lt);
-		}
-		__syncwarp();
-	}
-	__syncthreads();
-	// digit `tid`: per-warp exclusive offsets + tile total
-	uint32_t total = 0;
-#pragma unroll
-	for (int w = 0; w < 8; w++) { const uint32_t c = s_whist[w][tid]; s_whist[w][tid] = total; total += c; }
-	// chained scan over tiles (decoupled look-back) for digit `tid`
-	uint32_t excl = 0;
-	if (tile == 0) lookback[tid] = LB_INC | total;
-	else
-	{
-		atomicExch(&lookback[(size_t)tile * 256 + tid], LB_AGG | total);
-		long long j = (long long)tile - 1;
-		while (true)
-		{
-			uint32_t c;
-			do { c = *reinterpret_cast<volatile uint32_t*>(&lookback[(size_t)j * 256 + tid]); } while (c == 0);
-			excl += c & LB_VAL;
-			if (c & LB_INC) break;
-			j--;
-		}
-		atomicExch(&lookback[(size_t)tile * 256 + tid], LB_INC | (excl + total));
-	}
-	// tile-local exclusive scan of digit totals (256 entries) -> s_dstart
-	s_dstart[tid] = total;
-	__syncthreads();
-	for (int o = 1; o < 256; o <<= 1)
-	{
-		const uint32_t t = tid >= o ? s_dstart[tid - o] : 0u;
+		const uint32_t tile = LIST ? cls_list[wi] : wi;
+		const uint2 r = ranges[tile];
+		const uint32_t n = r.y - r.x;
+		if (n == 0 || n > (uint32_t)CAP) continue;
+		if (n == 1) { if (tid == 0) point_list[r.x] = (uint32_t)bucket[r.x]; continue; }
+		if (tid == 0) { s_and = 0xffffffffu; s_or = 0u; }
 		__syncthreads();
-		s_dstart[tid] += t;
+		uint32_t a_and = 0xffffffffu, a_or = 0u;
+		for (uint32_t i = tid; i < n; i += THREADS)
+		{
+			const uint64_t c = bucket[r.x + i];
+			const uint32_t k = (uint32_t)(c >> 32);
+			kA[i] = k; vA[i] = (uint32_t)c;
+			a_and &= k; a_or |= k;
+		}
+		a_and = __reduce_and_sync(0xffffffffu, a_and); a_or = __reduce_or_sync(0xffffffffu, a_or);
+		if (lane == 0) { atomicAnd(&s_and, a_and); atomicOr(&s_or, a_or); }
 		__syncthreads();
-	}
-	const uint32_t dstart = s_dstart[tid] - total;
-	__syncthreads();
-	s_dstart[tid] = dstart;
-	s_gbase[tid] = plan->digit_base[pass][tid] + excl - dstart;    // global index = s_gbase[d] + tile-local sorted position
-	__syncthreads();
-	// scatter keys into tile-local sorted order
-	uint32_t pos[SORT_ITEMS];
-#pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++)
-	{
-		const int local = warp * (32 * SORT_ITEMS) + i * 32 + lane;
-		if (local < count)
+		const uint32_t differ = s_and ^ s_or;       // bits in which the tile's keys are not all equal
+		uint32_t* ks = kA; uint32_t* vs = vA; uint32_t* kd = kB; uint32_t* vd = vB;
+		for (int pass = 0; pass < 4; pass++)
 		{
-			const uint32_t d = (uint32_t)((key[i] >> shift) & 0xff);
-			pos[i] = s_dstart[d] + s_whist[warp][d] + rank[i];
-			s_keys[pos[i]] = key[i];
-		}
-	}
-	__syncthreads();
-	uint32_t gpos[SORT_ITEMS];
+			const int shift = 8 * pass;
+			if (((differ >> shift) & 0xffu) == 0) continue;         // every key has the same digit: the pass is the identity
+			for (int i = tid; i < NW * 256; i += THREADS) whist[i] = 0;
+			__syncthreads();
+			uint32_t key[ITEMS], val[ITEMS], rank[ITEMS];
 #pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++)
-	{
-		const int p = i * SORT_THREADS + tid;
-		if (p < count)
+			for (int i = 0; i < ITEMS; i++)
+			{
+				const uint32_t pos = warp * (32 * ITEMS) + i * 32 + lane;
+				const bool valid = pos < n;
+				key[i] = valid ? ks[pos] : 0u; val[i] = valid ? vs[pos] : 0u;
+				const uint32_t d = valid ? (key[i] >> shift) & 0xffu : 256u;
+				const unsigned vm = __ballot_sync(0xffffffffu, valid);
+				if (vm == 0) { rank[i] = 0; continue; }
+				const unsigned m = __match_any_sync(0xffffffffu, d) & vm;
+				if (valid)
+				{
+					const int leader = __ffs(m) - 1;
+					uint32_t old = 0;
+					if (lane == leader) { old = whist[warp * 256 + d]; whist[warp * 256 + d] = old + __popc(m); }
+					old = __shfl_sync(m, old, leader);
+					rank[i] = old + __popc(m & lt);
+				}
+				__syncwarp();
+			}
+			__syncthreads();
+			// digit `tid` (< 256): per-warp exclusive offsets, then an exclusive scan of the digit totals
+			uint32_t total = 0;
+			if (tid < 256)
+			{
+#pragma unroll 4
+				for (int w = 0; w < NW; w++) { const uint32_t c = whist[w * 256 + tid]; whist[w * 256 + tid] = total; total += c; }
+				uint32_t incl = total;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+				if (lane == 31) s_wtot[warp] = incl;
+				s_dstart[tid] = incl - total;
+			}
+			__syncthreads();
+			if (tid < 256)
+			{
+				uint32_t add = 0;
+#pragma unroll
+				for (int w = 0; w < 8; w++) if (w < warp) add += s_wtot[w];
+				s_dstart[tid] += add;
+			}
+			__syncthreads();
+#pragma unroll
+			for (int i = 0; i < ITEMS; i++)
+			{
+				const uint32_t pos = warp * (32 * ITEMS) + i * 32 + lane;
+				if (pos < n)
+				{
+					const uint32_t d = (key[i] >> shift) & 0xffu;
+					const uint32_t np = s_dstart[d] + whist[warp * 256 + d] + rank[i];
+					kd[np] = key[i]; vd[np] = val[i];
+				}
+			}
+			__syncthreads();
+			uint32_t* t0 = ks; ks = kd; kd = t0; t0 = vs; vs = vd; vd = t0;
+		}
+		// runs of bit-identical depths (rare): ascending Gaussian id, as the reference's stable sort leaves them
+		for (uint32_t p = tid; p < n; p += THREADS)
 		{
-			const uint64_t k = s_keys[p];
-			gpos[i] = s_gbase[(uint32_t)((k >> shift) & 0xff)] + p;
-			kout[gpos[i]] = k;
+			const uint32_t k = ks[p];
+			if ((p == 0 || ks[p - 1] != k) && p + 1 < n && ks[p + 1] == k)
+			{
+				uint32_t e = p + 1;
+				while (e < n && ks[e] == k) e++;
+				for (uint32_t i = p + 1; i < e; i++)
+				{
+					const uint32_t v = vs[i];
+					uint32_t j = i;
+					while (j > p && vs[j - 1] > v) { vs[j] = vs[j - 1]; j--; }
+					vs[j] = v;
+				}
+			}
 		}
-	}
-	__syncthreads();
-	// values: load in the original arrangement, route through the same tile-local positions
-#pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++)
-	{
-		const int local = warp * (32 * SORT_ITEMS) + i * 32 + lane;
-		if (local < count) s_vals[pos[i]] = vin[tbase + local];
-	}
-	__syncthreads();
-#pragma unroll
-	for (int i = 0; i < SORT_ITEMS; i++)
-	{
-		const int p = i * SORT_THREADS + tid;
-		if (p < count) vout[gpos[i]] = s_vals[p];
+		__syncthreads();
+		for (uint32_t i = tid; i < n; i += THREADS) point_list[r.x + i] = vs[i];
+		__syncthreads();
 	}
 }
 
-// identifyTileRanges (rasterizer_impl.cu:124-146); ranges zeroed by the caller (cudaMemsetAsync).
-__global__ void __launch_bounds__(256) tile_ranges_kernel(long long L, const uint64_t* keys0, const uint64_t* keys1,
-	const SortPlan* __restrict__ plan, uint2* __restrict__ ranges)
+// Segments beyond the shared-memory classes: single-CTA stable LSD radix sort (8 x 8-bit digits of the 64-bit
+// composite) ping-ponging between the bucket and its spare copy in global memory.  Rare (very dense tiles).
+__global__ void __launch_bounds__(1024) tile_sort_big_kernel(const uint2* __restrict__ ranges, uint64_t* bucket, uint64_t* alt,
+	uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cls_list, const uint32_t* __restrict__ cls_count)
 {
-	const uint64_t* __restrict__ keys = plan->final_buf ? keys1 : keys0;
-	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= L) return;
-	const uint32_t cur = (uint32_t)(keys[idx] >> 32);
-	if (idx == 0) ranges[cur].x = 0;
-	else
+	__shared__ uint32_t s_base[256];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for (uint32_t wi = blockIdx.x; wi < *cls_count; wi += gridDim.x)
 	{
-		const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
-		if (cur != prev) { ranges[prev].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
+	const uint2 r = ranges[cls_list[wi]];
+	const uint32_t n = r.y - r.x;
+	uint64_t* src = bucket + r.x;
+	uint64_t* dst = alt + r.x;
+	__syncthreads();
+	for (int pass = 0; pass < 8; pass++)
+	{
+		const int shift = 8 * pass;
+		if (tid < 256) s_base[tid] = 0;
+		__syncthreads();
+		for (uint32_t i = tid; i < n; i += 1024) atomicAdd(&s_base[(uint32_t)(src[i] >> shift) & 0xff], 1u);
+		__syncthreads();
+		if (tid == 0) { uint32_t run = 0; for (int d = 0; d < 256; d++) { const uint32_t c = s_base[d]; s_base[d] = run; run += c; } }
+		__syncthreads();
+		// stable scatter, 1024 elements at a time; warps take turns (ranks inside a warp from match.any)
+		for (uint32_t c0 = 0; c0 < n; c0 += 1024)
+		{
+			const uint32_t i = c0 + tid;
+			const bool valid = i < n;
+			const uint64_t key = valid ? src[i] : 0ull;
+			const uint32_t d = valid ? (uint32_t)(key >> shift) & 0xff : 256u;
+			for (int w = 0; w < 32; w++)
+			{
+				if (warp == w)
+				{
+					const unsigned vm = __ballot_sync(0xffffffffu, valid);
+					const unsigned m = __match_any_sync(0xffffffffu, d) & vm;
+					if (valid)
+					{
+						const int leader = __ffs(m) - 1;
+						uint32_t old = 0;
+						if (lane == leader) { old = s_base[d]; s_base[d] = old + __popc(m); }
+						old = __shfl_sync(m, old, leader);
+						dst[old + __popc(m & ((1u << lane) - 1u))] = key;
+					}
+				}
+				__syncthreads();
+			}
+		}
+		__threadfence_block();
+		__syncthreads();
+		uint64_t* tmp = src; src = dst; dst = tmp;
 	}
-	if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+	// after 8 passes the data is back in `bucket`
+	for (uint32_t i = tid; i < n; i += 1024) point_list[r.x + i] = (uint32_t)src[i];
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
-static uint32_t higher_msb(uint32_t n)        // rasterizer_impl.cu:41-58 getHigherMsb
+int launch_tile_scan(const ImageState& img, const GeomState& g, int W, int H, cudaStream_t stream)
 {
-	uint32_t msb = sizeof(n) * 4, step = msb;
-	while (step > 1) { step /= 2; if (n >> msb) msb += step; else msb -= step; }
-	if (n >> msb) msb++;
-	return msb;
-}
-
-int launch_scan(const GeomState& g, int P, cudaStream_t stream)
-{
-	const int blocks = (P + 256 * SCAN_ITEMS - 1) / (256 * SCAN_ITEMS);
+	const int T = ((W + GSB_TILE_X - 1) / GSB_TILE_X) * ((H + GSB_TILE_Y - 1) / GSB_TILE_Y);
 	ProfScope prof(K_SCAN, stream);
-	scan_kernel<<<blocks, 256, 0, stream>>>(g.tiles_touched, g.point_offsets, P, g.scan_state, g.counters);
+	tile_scan_kernel<<<1, 1024, 0, stream>>>(img.tile_count, T, img.ranges, g.counters, img.tile_cursor, img.cls_list, img.cls_count);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
 	return GSB_OK;
 }
 
-int launch_binning(const GeomState& g, const BinningState& b, char* bin_blob, const ImageState& img, int P, long long R, int W, int H, cudaStream_t stream)
+int launch_binning(const GeomState& g, const BinningState& b, const ImageState& img, int P, long long R, int W, int H, cudaStream_t stream)
 {
+	if (R == 0) return GSB_OK;
 	const int gx = (W + GSB_TILE_X - 1) / GSB_TILE_X, gy = (H + GSB_TILE_Y - 1) / GSB_TILE_Y;
-	GSB_CUDA_OK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
-	GSB_CUDA_OK(cudaMemsetAsync(bin_blob + b.zero_begin, 0, b.zero_bytes, stream));
-	sort_plan_init_kernel<<<1, 32, 0, stream>>>(b.plan);
-	GSB_LAUNCHED();
-	if (R == 0) { GSB_CUDA_OK(cudaGetLastError()); return GSB_OK; }
-	{ ProfScope prof(K_EMIT_KEYS, stream);
-	emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, g.tiles_touched, g.point_offsets, gx, b.keys[0], b.vals[0]); }
-	GSB_LAUNCHED();
-	const int bits = 32 + (int)higher_msb((uint32_t)(gx * gy));                        // rasterizer_impl.cu:465-473
-	const int passes = (bits + 7) / 8;
-	const size_t n_tiles = BinningState::sort_tiles(R);
-	const int hist_blocks = (int)((n_tiles < 148 * 8) ? n_tiles : 148 * 8);
-	{ ProfScope prof(K_SORT_HIST, stream);
-	sort_hist_kernel<<<hist_blocks, 256, 0, stream>>>(b.keys[0], R, passes, b.hist); }
-	GSB_LAUNCHED();
-	{ ProfScope prof(K_SORT_PLAN, stream);
-	sort_plan_kernel<<<1, 256, 0, stream>>>(b.hist, R, passes, b.plan); }
-	GSB_LAUNCHED();
-	for (int p = 0; p < passes; p++)
+	const int T = gx * gy;
 	{
-		ProfScope prof(K_SORT_PASS, stream);
-		sort_pass_kernel<<<(unsigned)n_tiles, SORT_THREADS, 0, stream>>>(b.keys[0], b.keys[1], b.vals[0], b.vals[1], R, p, b.plan,
-			b.lookback, b.tickets, n_tiles);
+		ProfScope prof(K_EMIT_KEYS, stream);
+		scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, img.ranges, img.tile_cursor, gx, b.bucket);
 		GSB_LAUNCHED();
 	}
-	{ ProfScope prof(K_TILE_RANGES, stream);
-	tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, b.keys[0], b.keys[1], b.plan, img.ranges); }
-	GSB_LAUNCHED();
+	constexpr size_t smemA = size_t(GSB_SORT_CAP_A) * 16 + 8 * 256 * 4, smemB = size_t(GSB_SORT_CAP_B) * 16 + 32 * 256 * 4;
+	static bool attr_set = false;
+	if (!attr_set)
+	{
+		GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<GSB_SORT_CAP_A, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+		GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<GSB_SORT_CAP_B, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+		attr_set = true;
+	}
+	{
+		ProfScope prof(K_SORT_PASS, stream);
+		tile_sort_kernel<GSB_SORT_CAP_A, 256, false><<<T, 256, smemA, stream>>>(img.ranges, b.bucket, b.point_list, nullptr, nullptr);
+		GSB_LAUNCHED();
+	}
+	{
+		ProfScope prof(K_SORT_LARGE, stream);
+		tile_sort_kernel<GSB_SORT_CAP_B, 1024, true><<<148, 1024, smemB, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list, img.cls_count);
+		GSB_LAUNCHED();
+		tile_sort_big_kernel<<<74, 1024, 0, stream>>>(img.ranges, b.bucket, b.alt, b.point_list, img.cls_list + T, img.cls_count + 1);
+		GSB_LAUNCHED();
+	}
+	GSB_CUDA_OK(cudaGetLastError());
+	return GSB_OK;
+}
+
+// Debug/tooling export in the reference's format: sorted keys (tile << 32 | depth bits) and the sorted id list.
+__global__ void export_binning_kernel(int T, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+	const float4* __restrict__ rec, uint64_t* keys, uint32_t* vals)
+{
+	const int tile = blockIdx.x;
+	if (tile >= T) return;
+	const uint2 r = ranges[tile];
+	for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x)
+	{
+		const uint32_t id = point_list[i];
+		if (keys) keys[i] = ((uint64_t)tile << 32) | __float_as_uint(rec[3 * (size_t)id + 2].z);
+		if (vals) vals[i] = id;
+	}
+}
+
+int launch_export_binning(const GeomState& g, const BinningState& b, const ImageState& img, int W, int H, uint64_t* keys, uint32_t* vals, cudaStream_t stream)
+{
+	const int T = ((W + GSB_TILE_X - 1) / GSB_TILE_X) * ((H + GSB_TILE_Y - 1) / GSB_TILE_Y);
+	export_binning_kernel<<<T, 128, 0, stream>>>(T, img.ranges, b.point_list, g.rec, keys, vals);
 	GSB_CUDA_OK(cudaGetLastError());
 	return GSB_OK;
 }

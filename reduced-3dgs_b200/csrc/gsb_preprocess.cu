@@ -18,7 +18,7 @@ struct PreArgs {
 	int packed; int cum[4]; long long group_base[4];   // packed SH: first vec3 index of each degree group
 	const uint8_t* prune;
 	int quant; GsbQuant q;
-	GeomState g; int32_t* radii;
+	GeomState g; int32_t* radii; uint32_t* tile_count;
 	GsbDebug dbg; int prefiltered;
 };
 
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 	{
 		const long long idx = base + threadIdx.x;
 		bool visible = false;
+		uint32_t my_tiles = 0; uint2 my_rect = make_uint2(0, 0);
 		if (idx < a.P)
 		{
 			uint32_t tiles = 0; int radius_i = 0;
@@ -226,9 +227,27 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 				if (a.dbg.clamped) { for (int c = 0; c < 3; c++) a.dbg.clamped[3 * idx + c] = (clamp_bits >> c) & 1u; }
 			} while (false);
 			a.radii[idx] = radius_i;
-			a.g.tiles_touched[idx] = tiles;
 			a.g.rect[idx] = rect;
 			if (a.dbg.tiles_touched) a.dbg.tiles_touched[idx] = tiles;
+			my_tiles = tiles; my_rect = rect;
+		}
+		// per-tile instance counts (what the reference derives from sorted keys in identifyTileRanges): one RED per
+		// (Gaussian, tile); Gaussians covering more than 32 tiles are spread over the warp
+		{
+			const uint32_t minx = my_rect.x & 0xffffu, maxx = my_rect.x >> 16, miny = my_rect.y & 0xffffu, maxy = my_rect.y >> 16;
+			const uint32_t w = maxx - minx;
+			const bool big = my_tiles > 32;
+			if (my_tiles && !big)
+				for (uint32_t y = miny; y < maxy; y++)
+					for (uint32_t x = minx; x < maxx; x++) atomicAdd(&a.tile_count[y * a.gx + x], 1u);
+			unsigned bigmask = __ballot_sync(0xffffffffu, big);
+			while (bigmask)
+			{
+				const int src = __ffs(bigmask) - 1; bigmask &= bigmask - 1;
+				const uint32_t bt = __shfl_sync(0xffffffffu, my_tiles, src), bw = __shfl_sync(0xffffffffu, w, src);
+				const uint32_t bminx = __shfl_sync(0xffffffffu, minx, src), bminy = __shfl_sync(0xffffffffu, miny, src);
+				for (uint32_t k = threadIdx.x & 31; k < bt; k += 32) atomicAdd(&a.tile_count[(bminy + k / bw) * a.gx + bminx + k % bw], 1u);
+			}
 		}
 		block_vis += __popc(__ballot_sync(0xffffffffu, visible)) * ((threadIdx.x & 31) == 0);
 	}
@@ -265,7 +284,7 @@ int launch_debug_dequant(const GsbQuant* q, int P, float* scales, float* rots, c
 	return GSB_OK;
 }
 
-int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& g, int32_t* radii, const GsbDebug* dbg, cudaStream_t stream)
+int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& g, uint32_t* tile_count, int32_t* radii, const GsbDebug* dbg, cudaStream_t stream)
 {
 	PreArgs a{};
 	a.P = s->P; a.M = s->M; a.W = cam->width; a.H = cam->height;
@@ -291,7 +310,7 @@ int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& 
 	a.prune = s->prune_mask;
 	a.quant = s->quant != nullptr;
 	if (s->quant) a.q = *s->quant;
-	a.g = g; a.radii = radii;
+	a.g = g; a.radii = radii; a.tile_count = tile_count;
 	if (dbg) a.dbg = *dbg;
 	a.prefiltered = cam->prefiltered;
 	const int blocks_needed = (s->P + 255) / 256;

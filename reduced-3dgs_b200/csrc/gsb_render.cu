@@ -22,17 +22,29 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Shared-memory staging record: 48 bytes per instance, r0 | r1 | (g, b, -, -); read with one address + immediate offsets.
+#define SREC_BYTES 48
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+	float2 v;
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+	return v;
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __restrict__ ranges,
-	const uint32_t* pl0, const uint32_t* pl1, const SortPlan* __restrict__ plan,
+	const uint32_t* __restrict__ point_list,
 	int W, int H, const float4* __restrict__ rec, const float* __restrict__ bg,
 	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, uint32_t* __restrict__ tile_max)
 {
-	__shared__ float4 s_r0[256];
-	__shared__ float4 s_r1[256];
-	__shared__ float2 s_r2[256];
+	__shared__ __align__(16) float4 s_rec[256 * 3];
 	__shared__ uint32_t s_max;
-	const uint32_t* __restrict__ point_list = plan->final_buf ? pl1 : pl0;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tile = blockIdx.y * gridDim.x + blockIdx.x;
 	const int wx0 = blockIdx.x * GSB_TILE_X + (warp & 1) * 8, wy0 = blockIdx.y * GSB_TILE_Y + (warp >> 1) * 4;
@@ -41,6 +53,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 	const float pxf = (float)px, pyf = (float)py;
 	const float rx0 = (float)wx0, rx1 = (float)(wx0 + 7), ry0 = (float)wy0, ry1 = (float)(wy0 + 3);
 	const uint2 range = ranges[tile];
+	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_rec);
 	if (tid == 0) s_max = 0;
 
 	bool done = !inside;
@@ -54,7 +67,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 		{
 			const uint32_t id = point_list[b + tid];
 			const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
-			s_r0[tid] = r0; s_r1[tid] = r1; s_r2[tid] = make_float2(r2.x, r2.y);
+			s_rec[3 * tid] = r0; s_rec[3 * tid + 1] = r1; s_rec[3 * tid + 2] = r2;
 		}
 		__syncthreads();
 		bool warp_done = __all_sync(0xffffffffu, done);
@@ -64,30 +77,36 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 			bool keep = false;
 			if (j < n)
 			{
-				const float4 r0 = s_r0[j]; const float4 r1 = s_r1[j];
+				const float4 r0 = lds128(sbase + j * SREC_BYTES), r1 = lds128(sbase + j * SREC_BYTES + 16);
 				keep = rect_may_contribute(r1.x, r1.y, r0.x, r0.y, r0.z, r0.w, rx0, rx1, ry0, ry1);
 			}
 			unsigned mask = __ballot_sync(0xffffffffu, keep);
+			const uint32_t cbase = sbase + c0 * SREC_BYTES;
+			const uint32_t nbase = (b - range.x) + c0 + 1;          // 1-based list position of the chunk's first entry
+			// Branch-free per-pixel body: in a surviving warp some lane nearly always takes every path of the reference's
+			// if/continue chain, so predicating costs nothing and removes the divergence bookkeeping.  The arithmetic and
+			// the order of the tests are the reference's (forward.cu:535-569); a masked lane changes no state.
 			while (mask)
 			{
-				const int jj = c0 + __ffs(mask) - 1; mask &= mask - 1;
-				if (done) continue;
-				const float4 r0 = s_r0[jj]; const float4 r1 = s_r1[jj];
+				const int bit = __ffs(mask) - 1; mask &= mask - 1;
+				const uint32_t addr = cbase + bit * SREC_BYTES;
+				const float4 r0 = lds128(addr), r1 = lds128(addr + 16);
+				const float2 gb = lds64(addr + 32);
 				const float dx = __fsub_rn(r1.x, pxf), dy = __fsub_rn(r1.y, pyf);
 				const float power = pair_power(r0.x, r0.y, r0.z, dx, dy);
-				// power > 0: reference `continue`; power < pth: alpha = opacity*exp(power) is provably < 1/255 (the
-				// reference's other `continue`), so the exp is skipped for most evaluated pairs
-				if (power > 0.0f || power < r0.w) continue;
+				// power > 0: reference `continue`; power < pth: alpha = opacity*exp(power) is provably < 1/255
+				bool v = !done && !(power > 0.0f) && !(power < r0.w);
 				const float alpha = fminf(0.99f, __fmul_rn(r1.z, exp_ref(power)));
-				if (alpha < 1.0f / 255.0f) continue;
+				v = v && !(alpha < 1.0f / 255.0f);
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-				if (test_T < 0.0001f) { done = true; continue; }
-				const float2 gb = s_r2[jj];
-				C0 = __fmaf_rn(T, __fmul_rn(r1.w, alpha), C0);
-				C1 = __fmaf_rn(T, __fmul_rn(gb.x, alpha), C1);
-				C2 = __fmaf_rn(T, __fmul_rn(gb.y, alpha), C2);
-				T = test_T;
-				last = (b - range.x) + jj + 1;
+				const bool stop = v && (test_T < 0.0001f);
+				done = done || stop;
+				v = v && !stop;
+				C0 = v ? __fmaf_rn(T, __fmul_rn(r1.w, alpha), C0) : C0;
+				C1 = v ? __fmaf_rn(T, __fmul_rn(gb.x, alpha), C1) : C1;
+				C2 = v ? __fmaf_rn(T, __fmul_rn(gb.y, alpha), C2) : C2;
+				T = v ? test_T : T;
+				last = v ? nbase + bit : last;
 			}
 			warp_done = __all_sync(0xffffffffu, done);
 		}
@@ -134,18 +153,15 @@ __device__ __forceinline__ float warp_reduce8(float v0, float v1, float v2, floa
 // sx = sum dL_dG*dG_ddelx, sy = sum dL_dG*dG_ddely, cxx = sum gdx*dx*dL_dG, cxy = sum gdx*dy*dL_dG, cyy = sum gdy*dy*dL_dG;
 // the constant factors (0.5*W, 0.5*H, -0.5) of backward.cu:583-589 are applied once per Gaussian by the consumer.
 __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __restrict__ ranges,
-	const uint32_t* pl0, const uint32_t* pl1, const SortPlan* __restrict__ plan,
+	const uint32_t* __restrict__ point_list,
 	int W, int H, const float4* __restrict__ rec, const float* __restrict__ bg,
 	const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_max,
 	const float* __restrict__ dL_dpixels, float* __restrict__ acc)
 {
-	__shared__ float4 s_r0[256];
-	__shared__ float4 s_r1[256];
-	__shared__ float2 s_r2[256];
+	__shared__ __align__(16) float4 s_rec[256 * 3];
 	__shared__ uint32_t s_id[256];
 	__shared__ float s_acc[256 * ACC_STRIDE];
 	__shared__ uint32_t s_touched[256];
-	const uint32_t* __restrict__ point_list = plan->final_buf ? pl1 : pl0;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tile = blockIdx.y * gridDim.x + blockIdx.x;
 	const uint32_t hi = tile_max[tile];
@@ -157,6 +173,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 	const float rx0 = (float)wx0, rx1 = (float)(wx0 + 7), ry0 = (float)wy0, ry1 = (float)(wy0 + 3);
 	const uint2 range = ranges[tile];
 	const size_t pid = (size_t)W * py + px, N = (size_t)W * H;
+	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_rec);
 
 	const float T_final = inside ? final_Ts[pid] : 0.0f;
 	float T = T_final;
@@ -177,7 +194,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 		{
 			const uint32_t id = point_list[range.x + (hi - 1 - b - tid)];
 			const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
-			s_r0[tid] = r0; s_r1[tid] = r1; s_r2[tid] = make_float2(r2.x, r2.y); s_id[tid] = id;
+			s_rec[3 * tid] = r0; s_rec[3 * tid + 1] = r1; s_rec[3 * tid + 2] = r2; s_id[tid] = id;
 		}
 #pragma unroll
 		for (int k = 0; k < ACC_STRIDE; k++) s_acc[k * 256 + tid] = 0.0f;   // plain zero fill of the [256][9] array
@@ -189,7 +206,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 			bool keep = false;
 			if (j < n && (hi - 1 - b - j) < wmax)
 			{
-				const float4 r0 = s_r0[j]; const float4 r1 = s_r1[j];
+				const float4 r0 = lds128(sbase + j * SREC_BYTES), r1 = lds128(sbase + j * SREC_BYTES + 16);
 				keep = rect_may_contribute(r1.x, r1.y, r0.x, r0.y, r0.z, r0.w, rx0, rx1, ry0, ry1);
 			}
 			unsigned mask = __ballot_sync(0xffffffffu, keep);
@@ -197,7 +214,8 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 			{
 				const int jj = c0 + __ffs(mask) - 1; mask &= mask - 1;
 				const uint32_t pos = hi - 1 - b - jj;
-				const float4 r0 = s_r0[jj]; const float4 r1 = s_r1[jj];
+				const uint32_t addr = sbase + jj * SREC_BYTES;
+				const float4 r0 = lds128(addr), r1 = lds128(addr + 16);
 				const float dx = __fsub_rn(r1.x, pxf), dy = __fsub_rn(r1.y, pyf);
 				bool active = pos < last_contributor;                                   // backward.cu:524-526
 				float G = 0.f, alpha = 0.f;
@@ -220,7 +238,7 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 					const float inv = __frcp_rn(one_m_alpha);
 					T = T * inv;                                                        // backward.cu:541
 					const float dchannel_dcolor = alpha * T;
-					const float2 gb = s_r2[jj];
+					const float2 gb = lds64(addr + 32);
 					const float cr = r1.w, cg = gb.x, cb = gb.y;
 					const float oml = 1.0f - last_alpha;
 					ar0 = last_alpha * lc0 + oml * ar0; lc0 = cr;
@@ -263,7 +281,7 @@ int launch_render_forward(const ImageState& img, const BinningState& b, const Ge
 {
 	const dim3 grid((W + GSB_TILE_X - 1) / GSB_TILE_X, (H + GSB_TILE_Y - 1) / GSB_TILE_Y);
 	ProfScope prof(K_RENDER_FWD, stream);
-	render_forward_kernel<<<grid, 256, 0, stream>>>(img.ranges, b.vals[0], b.vals[1], b.plan, W, H, g.rec, bg,
+	render_forward_kernel<<<grid, 256, 0, stream>>>(img.ranges, b.point_list, W, H, g.rec, bg,
 		img.final_T, img.n_contrib, out_color, img.tile_max_contrib);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
@@ -275,7 +293,7 @@ int launch_render_backward(const ImageState& img, const BinningState& b, const G
 {
 	const dim3 grid((W + GSB_TILE_X - 1) / GSB_TILE_X, (H + GSB_TILE_Y - 1) / GSB_TILE_Y);
 	ProfScope prof(K_RENDER_BWD, stream);
-	render_backward_kernel<<<grid, 256, 0, stream>>>(img.ranges, b.vals[0], b.vals[1], b.plan, W, H, g.rec, bg,
+	render_backward_kernel<<<grid, 256, 0, stream>>>(img.ranges, b.point_list, W, H, g.rec, bg,
 		img.final_T, img.n_contrib, img.tile_max_contrib, dL_dpix, acc);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());

@@ -180,7 +180,7 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     return present
 
 
-def export_state(geomBuffer, binningBuffer, imageBuffer, R, W, H):
+def export_state(geomBuffer, binningBuffer, imageBuffer, R, W, H, P=0):
     """Decode the private blobs into reference-layout arrays (tests / tooling)."""
     device = imageBuffer.device
     L = _lib.lib()
@@ -189,7 +189,8 @@ def export_state(geomBuffer, binningBuffer, imageBuffer, R, W, H):
         keys = torch.zeros(max(R, 0), dtype=torch.int64, device=device)
         pl = torch.zeros(max(R, 0), dtype=torch.int32, device=device)
         if R > 0:
-            _lib.check(L.gsb_export_binning(ptr(binningBuffer), int(R), ptr(keys), ptr(pl), _lib.current_stream(device)))
+            _lib.check(L.gsb_export_binning(ptr(geomBuffer), int(P), ptr(binningBuffer), int(R), ptr(imageBuffer), W, H,
+                                            ptr(keys), ptr(pl), _lib.current_stream(device)))
         T = ((W + 15) // 16) * ((H + 15) // 16)
         final_T = torch.zeros(H, W, device=device)
         n_contrib = torch.zeros(H, W, dtype=torch.int32, device=device)

@@ -95,7 +95,8 @@ def lib():
         L.gsb_mark_visible.restype = C.c_int
         L.gsb_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsb_export_binning.restype = C.c_int
-        L.gsb_export_binning.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsb_export_binning.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsb_export_image.restype = C.c_int
         L.gsb_export_image.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsb_debug_dequant.restype = C.c_int
@@ -162,7 +163,13 @@ class BlobAllocator:
         holder = []
 
         def alloc(_user, nbytes, _holder=holder, _device=device):
-            t = torch.empty(int(nbytes), dtype=torch.uint8, device=_device)
+            # round up to 1/16 of the next power of two: the instance count R changes a little from view to view, and the
+            # caching allocator can only reuse a block that is at least as large as the request
+            nbytes = int(nbytes)
+            if nbytes > (1 << 20):
+                q = 1 << (nbytes.bit_length() - 5)
+                nbytes = (nbytes + q - 1) // q * q
+            t = torch.empty(nbytes, dtype=torch.uint8, device=_device)
             _holder.append(t)
             return t.data_ptr()
 

@@ -32,7 +32,7 @@ def run_forward(scene, cam, bg, extra=None, prune_mask=None, quant=None, dev="cu
     out = _C.rasterize_gaussians(*args, prune_mask=None if prune_mask is None else prune_mask.to(dev),
                                  quant=None if quant is None else quant.to(dev), debug_out=dbg)
     R, color, radii, geomB, binB, imgB = out
-    st = _C.export_state(geomB, binB, imgB, R, cam.image_width, cam.image_height)
+    st = _C.export_state(geomB, binB, imgB, R, cam.image_width, cam.image_height, P=scene.means3D.shape[0])
     torch.cuda.synchronize()
     res = dict(num_rendered=R, color=color.cpu().numpy(), radii=radii.cpu().numpy(),
                depths=dbg["depths"].cpu().numpy(), means2D=dbg["means2D"].cpu().numpy(), cov3D=dbg["cov3D"].cpu().numpy(),
