@@ -42,7 +42,9 @@ def test_forward_integers_bit_exact(case):
 def test_forward_floats(case):
     name, ref, fwd, _ = case
     vis = ref["radii"] > 0
-    for k in ("depths", "means2D", "cov3D", "rgb", "clamped"):
+    # with precomputed covariance / colours the reference never writes its own cov3D / rgb / clamped slots (garbage in the blob)
+    keys = ("depths", "means2D") if cases.CASES[name]["precomp"] else ("depths", "means2D", "cov3D", "rgb", "clamped")
+    for k in keys:
         assert np.array_equal(ref[k][vis], fwd[k][vis]), k
     assert np.array_equal(ref["conic_opacity"][vis, :3], fwd["conic_opacity"][vis, :3])
     a, b = ref["conic_opacity"][vis, 3], fwd["conic_opacity"][vis, 3]
