@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 		const uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
 		if (t < T)
 		{
-			ranges[t] = make_uint2(start, start + c); cursor[t] = 0;
+			ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);   // empty tiles stay (0,0) as after the reference's memset (RI:475)
+			cursor[t] = 0;
 			// tiles too large for the one-CTA-per-tile class are queued for the persistent large-segment kernels
 			if (c > GSB_SORT_CAP_A) { const int k = c > GSB_SORT_CAP_B; cls_list[k * T + atomicAdd(&cls_count[k], 1u)] = t; }
 		}
@@ -114,6 +115,7 @@ template <int CAP, int THREADS, bool LIST>
 __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
 	uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cls_list, const uint32_t* __restrict__ cls_count)
 {
+	// LIST == false: cls_list is the per-tile flag array written by tile_sort_dist_kernel (only flagged tiles are sorted here)
 	constexpr int ITEMS = CAP / THREADS, NW = THREADS / 32;
 	extern __shared__ __align__(16) unsigned char s_raw[];
 	uint32_t* kA = reinterpret_cast<uint32_t*>(s_raw);
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restr
 	for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x)
 	{
 		const uint32_t tile = LIST ? cls_list[wi] : wi;
+		if (!LIST && cls_list[tile] == 0) continue;
 		const uint2 r = ranges[tile];
 		const uint32_t n = r.y - r.x;
 		if (n == 0 || n > (uint32_t)CAP) continue;
@@ -235,6 +238,105 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restr
 	}
 }
 
+// Fast path for tiles of up to CAP_A instances: ONE-pass distribution sort.  Depth keys inside a tile are spread over a
+// narrow range, so binning them by (key - min) >> shift into 2048 order-preserving bins leaves ~1 key per bin; a per-bin
+// insertion sort on the full 64-bit composite (depth bits, id) then finishes the total order.  Tiles whose depths cluster
+// (some bin > 32 keys) are flagged and handled by the radix kernel below, so the result never depends on the heuristic.
+#define DIST_BINS 2048
+__global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
+	uint32_t* __restrict__ point_list, uint32_t* __restrict__ fallback_flag)
+{
+	__shared__ uint32_t s_bin[DIST_BINS];
+	__shared__ __align__(16) uint64_t s_out[GSB_SORT_CAP_A];
+	__shared__ uint32_t s_wtot[8];
+	__shared__ uint32_t s_min, s_max, s_big;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t tile = blockIdx.x;
+	const uint2 r = ranges[tile];
+	const uint32_t n = r.y - r.x;
+	if (tid == 0) fallback_flag[tile] = 0;
+	if (n == 0 || n > GSB_SORT_CAP_A) return;
+	if (n == 1) { if (tid == 0) point_list[r.x] = (uint32_t)bucket[r.x]; return; }
+	if (tid == 0) { s_min = 0xffffffffu; s_max = 0u; s_big = 0u; }
+	for (int i = tid; i < DIST_BINS; i += 256) s_bin[i] = 0;
+	__syncthreads();
+	uint64_t c[8];
+	uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+	{
+		const uint32_t p = i * 256 + tid;
+		c[i] = p < n ? bucket[r.x + p] : ~0ull;
+		if (p < n) { const uint32_t k = (uint32_t)(c[i] >> 32); kmin = min(kmin, k); kmax = max(kmax, k); }
+	}
+	kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+	if (lane == 0) { atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+	__syncthreads();
+	const uint32_t lo = s_min, range = s_max - lo;
+	const int shift = max(0, (32 - __clz(range)) - 11);              // (range >> shift) < 2048
+	uint32_t slot[8];
+	uint32_t worst = 0;
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+	{
+		const uint32_t p = i * 256 + tid;
+		if (p < n)
+		{
+			const uint32_t b = ((uint32_t)(c[i] >> 32) - lo) >> shift;
+			const uint32_t q = atomicAdd(&s_bin[b], 1u);
+			slot[i] = (b << 16) | q;
+			worst = max(worst, q);
+		}
+	}
+	if (__any_sync(0xffffffffu, worst >= 32)) { if (lane == 0) s_big = 1; }
+	__syncthreads();
+	if (s_big) { if (tid == 0) fallback_flag[tile] = 1; return; }
+	// exclusive scan of the 2048 bin counts: thread t owns bins [8t, 8t+8)
+	uint32_t cnt[8], local = 0;
+#pragma unroll
+	for (int i = 0; i < 8; i++) { cnt[i] = s_bin[8 * tid + i]; local += cnt[i]; }
+	uint32_t incl = local;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+	if (lane == 31) s_wtot[warp] = incl;
+	__syncthreads();
+	uint32_t start = incl - local;
+#pragma unroll
+	for (int w = 0; w < 8; w++) if (w < warp) start += s_wtot[w];
+	{
+		uint32_t run = start;
+#pragma unroll
+		for (int i = 0; i < 8; i++) { s_bin[8 * tid + i] = run; run += cnt[i]; }
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+	{
+		const uint32_t p = i * 256 + tid;
+		if (p < n) s_out[s_bin[slot[i] >> 16] + (slot[i] & 0xffffu)] = c[i];
+	}
+	__syncthreads();
+	// finish each of this thread's bins (ascending composite = depth bits, then Gaussian id)
+	{
+		uint32_t run = start;
+#pragma unroll
+		for (int i = 0; i < 8; i++)
+		{
+			const uint32_t m = cnt[i];
+			for (uint32_t a = 1; a < m; a++)
+			{
+				const uint64_t v = s_out[run + a];
+				uint32_t j = a;
+				while (j > 0 && s_out[run + j - 1] > v) { s_out[run + j] = s_out[run + j - 1]; j--; }
+				s_out[run + j] = v;
+			}
+			run += m;
+		}
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < n; i += 256) point_list[r.x + i] = (uint32_t)s_out[i];
+}
+
 // Segments beyond the shared-memory classes: single-CTA stable LSD radix sort (8 x 8-bit digits of the 64-bit
 // composite) ping-ponging between the bucket and its spare copy in global memory.  Rare (very dense tiles).
 __global__ void __launch_bounds__(1024) tile_sort_big_kernel(const uint2* __restrict__ ranges, uint64_t* bucket, uint64_t* alt,
@@ -323,7 +425,12 @@ int launch_binning(const GeomState& g, const BinningState& b, const ImageState& 
 	}
 	{
 		ProfScope prof(K_SORT_PASS, stream);
-		tile_sort_kernel<GSB_SORT_CAP_A, 256, false><<<T, 256, smemA, stream>>>(img.ranges, b.bucket, b.point_list, nullptr, nullptr);
+		tile_sort_dist_kernel<<<T, 256, 0, stream>>>(img.ranges, b.bucket, b.point_list, img.tile_cursor);   // cursors are dead after the scatter: reused as flags
+		GSB_LAUNCHED();
+	}
+	{
+		ProfScope prof(K_SORT_LARGE, stream);
+		tile_sort_kernel<GSB_SORT_CAP_A, 256, false><<<T, 256, smemA, stream>>>(img.ranges, b.bucket, b.point_list, img.tile_cursor, nullptr);
 		GSB_LAUNCHED();
 	}
 	{

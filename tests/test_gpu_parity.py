@@ -163,6 +163,51 @@ def test_edge_cases():
     assert np.abs(o["color"] - fwd["color"]).max() <= 1e-4
 
 
+@pytest.mark.parametrize("kind", ["ties", "dense_4k", "dense_12k", "dense_40k"])
+def test_sort_paths_ties_and_dense_tiles(kind):
+    """Every branch of the per-tile sort: bit-identical depths (tie order = ascending Gaussian id, as the reference's stable
+    sort leaves them), clustered depths (distribution-sort fallback), and tiles with > 2048 / > 8192 instances
+    (persistent shared-memory class and the global-memory fallback).  Integers must equal the oracle exactly."""
+    ours = _ours()
+    g = torch.Generator().manual_seed(7)
+    if kind == "ties":
+        P, W, H = 30_000, 128, 128
+        xyz = torch.rand(P, 3, generator=g) * 2 - 1
+        xyz[:, 2] = 0.0                                  # one plane facing the camera: identical view-space depth
+        xyz[::3, 2] = 0.25                               # ... and a second plane
+        scale = 0.02
+    else:
+        P = {"dense_4k": 12_000, "dense_12k": 40_000, "dense_40k": 120_000}[kind]
+        W, H = 64, 48
+        xyz = (torch.rand(P, 3, generator=g) * 2 - 1) * torch.tensor([0.5, 0.4, 1.0])
+        scale = 0.01
+    scales = torch.full((P, 3), scale) * (0.5 + torch.rand(P, 3, generator=g))
+    q = torch.nn.functional.normalize(torch.randn(P, 4, generator=g))
+    op = torch.randn(P, 1, generator=g) - 2.0
+    sh = torch.randn(P, 1, 3, generator=g)
+    deg = torch.zeros(P, 1, dtype=torch.int32)
+    scene = synth.Scene(xyz.contiguous(), op, scales.contiguous(), q.contiguous(), sh, deg)
+    cam = synth.make_camera(W, H)
+    bg = torch.zeros(3)
+    args, out, fwd = ours.run_forward(scene, cam, bg)
+    o = gs_oracle.forward(xyz, op, scales, q, sh, deg, bg=bg, **cam_kw(cam, W, H))
+    assert fwd["num_rendered"] == o["num_rendered"]
+    counts = (o["ranges"][:, 1] - o["ranges"][:, 0]).astype(np.int64)
+    if kind == "dense_4k":
+        assert counts.max() > 2048
+    if kind == "dense_12k":
+        assert counts.max() > 8192
+    if kind == "ties":
+        k = o["keys"]
+        assert (k[1:] == k[:-1]).sum() > 1000, "the case must contain many exact depth ties"
+    for k in ("radii", "keys", "point_list", "ranges"):
+        assert np.array_equal(np.asarray(o[k]).reshape(-1), fwd[k].reshape(-1)), k
+    nb = ~o["borderline"]          # pixels where a MUFU.EX2-vs-exp2f ulp can legitimately flip a threshold of the CPU oracle
+    assert np.array_equal(o["n_contrib"][nb], fwd["n_contrib"][nb]), "n_contrib"
+    assert (~nb).mean() < 5e-3
+    assert np.abs(o["color"] - fwd["color"])[:, nb].max() <= 1e-4
+
+
 def test_prune_mask_equals_compacted_scene():
     """Fused mask == reference semantics (rows physically deleted, gaussian_model.py:553-563), indices remapped."""
     ours = _ours()
