@@ -268,7 +268,7 @@ def main():
         launches0 = gsl.launch_count()
     sampler = ClockSampler(physical_gpu_index(local))
     barrier()
-    if rank == 0:
+    if rank == 0 and not os.environ.get("GS_BENCH_NO_CLOCKS"):
         sampler.start()
     evs = []
     for i in range(K):
@@ -287,7 +287,7 @@ def main():
         torch.cuda.synchronize()
         coll_ms = e0.elapsed_time(e1)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = (sampler.stop() if sampler._thread is not None or sampler.nv is None else {"sm_mhz": None, "reasons": ["sampling disabled"]}) if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(step_ms) + coll_ms
     if world > 1 and args.impl == "ours":

@@ -131,49 +131,72 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sum 8 per-lane values over the warp with a transposed butterfly: afterwards lane l holds the total of value
-// (l >> 2) & 7.  4+2+1 exchange shuffles + 2 plain ones instead of 8 x 5.
-__device__ __forceinline__ float warp_reduce8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, int lane)
+// Backward.  For one Gaussian and the 32 pixels of a warp the reference accumulates 9 sums (backward.cu:561-592).  With
+//     u_p = alpha_p * T_p                 (dL/dcolour weight)        w_p = G_p * dL/dalpha_p
+// and d = (X - px, Y - py) (X, Y = Gaussian centre, px, py = pixel, all tile-local) they are
+//     dL/dcolour_c = sum_p u_p * dLdpix_c(p)            dL/dopacity = sum_p w_p =: M0
+//     sum_p w_p dx   = X M0 - Mx        sum_p w_p dx^2  = X^2 M0 - 2X Mx + Mxx      (Mx = sum_p w_p px, ... the moments of w)
+// i.e. [Gaussians x pixels] . [pixels x 9 per-pixel constants]: a tiny matrix product.  The kernel therefore stashes
+// (w, u) for up to 16 surviving Gaussians per warp and lets the tensor cores do the pixel sums with 3xTF32-split
+// m16n8k8 MMAs (fp32-level accuracy: operands are split hi/lo, the per-pixel weights 1, px, py, px^2, px*py, py^2 are exact in
+// TF32), instead of a 14-shuffle butterfly + 9 products per (warp, Gaussian).  tcgen05 is not applicable to a per-warp
+// 16x32x8 product (it needs 64/128-row tiles from shared-memory descriptors and TMEM); this is the warp-level MMA path.
+#define BWD_BATCH 96
+#define STASH_LD 36            // row stride of the (w, u) stash: conflict-free A-fragment loads
+#define ACC_STRIDE 9           // per staged Gaussian: [dcol0 dcol1 dcol2 M0 Mx My Mxx Mxy Myy]
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
-	const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-	float a0 = (b4 ? v4 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v4, 16);
-	float a1 = (b4 ? v5 : v1) + __shfl_xor_sync(0xffffffffu, b4 ? v1 : v5, 16);
-	float a2 = (b4 ? v6 : v2) + __shfl_xor_sync(0xffffffffu, b4 ? v2 : v6, 16);
-	float a3 = (b4 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, b4 ? v3 : v7, 16);
-	float c0 = (b3 ? a2 : a0) + __shfl_xor_sync(0xffffffffu, b3 ? a0 : a2, 8);
-	float c1 = (b3 ? a3 : a1) + __shfl_xor_sync(0xffffffffu, b3 ? a1 : a3, 8);
-	float d = (b2 ? c1 : c0) + __shfl_xor_sync(0xffffffffu, b2 ? c0 : c1, 4);
-	d += __shfl_xor_sync(0xffffffffu, d, 2);
-	d += __shfl_xor_sync(0xffffffffu, d, 1);
-	return d;   // value index = 4*b4 + 2*b3 + b2
+	asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+		: "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo)
+{
+	hi = __float_as_uint(v) & 0xffffe000u;                    // the MMA reads the top 19 bits: truncation is a valid TF32
+	lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
-#define ACC_STRIDE 9
-// acc record (12 floats per Gaussian, 48 B): [dcol.r dcol.g dcol.b dop | sx sy cxx cxy | cyy - - -] where
+// acc record written for the preprocess backward (12 floats per Gaussian, 48 B): [dcol.r dcol.g dcol.b dop | sx sy cxx cxy | cyy - - -]
 // sx = sum dL_dG*dG_ddelx, sy = sum dL_dG*dG_ddely, cxx = sum gdx*dx*dL_dG, cxy = sum gdx*dy*dL_dG, cyy = sum gdy*dy*dL_dG;
 // the constant factors (0.5*W, 0.5*H, -0.5) of backward.cu:583-589 are applied once per Gaussian by the consumer.
-__global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __restrict__ ranges,
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct BwdSmem {
+	float4 rec[2][BWD_BATCH * 3];          // double-buffered staging of the tile's list (cp.async gather, one batch ahead)
+	uint32_t id[2][BWD_BATCH];
+	float w[8][16 * STASH_LD];
+	float u[8][16 * STASH_LD];
+	float4 rowinfo[8][16 * 2];            // per stashed row: (conic.xyz, id bits), (mean2D.xy, opacity, -): rows outlive their staging buffer
+	float dlp[8][3 * 32];                  // dL/dpixel of the warp's 32 pixels, channel-major: B operand of the colour product
+	float wgt[8 * 32];                     // (1, qx, qy, qx^2, qx*qy, qy^2, 0, 0) of the 32 warp-local pixels: B operand of the moment product
+};
+
+__global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __restrict__ ranges,
 	const uint32_t* __restrict__ point_list,
 	int W, int H, const float4* __restrict__ rec, const float* __restrict__ bg,
 	const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_max,
 	const float* __restrict__ dL_dpixels, float* __restrict__ acc)
 {
-	__shared__ __align__(16) float4 s_rec[256 * 3];
-	__shared__ uint32_t s_id[256];
-	__shared__ float s_acc[256 * ACC_STRIDE];
-	__shared__ uint32_t s_touched[256];
+	extern __shared__ __align__(16) unsigned char s_dyn_raw[];
+	BwdSmem& S = *reinterpret_cast<BwdSmem*>(s_dyn_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tile = blockIdx.y * gridDim.x + blockIdx.x;
 	const uint32_t hi = tile_max[tile];
 	if (hi == 0) return;
-	const int wx0 = blockIdx.x * GSB_TILE_X + (warp & 1) * 8, wy0 = blockIdx.y * GSB_TILE_Y + (warp >> 1) * 4;
-	const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);       // tile-local pixel of this lane
+	const int tx0 = blockIdx.x * GSB_TILE_X, ty0 = blockIdx.y * GSB_TILE_Y;
+	const int px = tx0 + lx, py = ty0 + ly;
 	const bool inside = px < W && py < H;
 	const float pxf = (float)px, pyf = (float)py;
-	const float rx0 = (float)wx0, rx1 = (float)(wx0 + 7), ry0 = (float)wy0, ry1 = (float)(wy0 + 3);
+	const float rx0 = (float)(tx0 + (warp & 1) * 8), rx1 = rx0 + 7.0f, ry0 = (float)(ty0 + (warp >> 1) * 4), ry1 = ry0 + 3.0f;
 	const uint2 range = ranges[tile];
 	const size_t pid = (size_t)W * py + px, N = (size_t)W * H;
-	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_rec);
+	const uint32_t sbase0 = (uint32_t)__cvta_generic_to_shared(&S.rec[0][0]);
 
 	const float T_final = inside ? final_Ts[pid] : 0.0f;
 	float T = T_final;
@@ -186,20 +209,119 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
 
-	for (uint32_t b = 0; b < hi; b += 256)
+	// B fragments (m16n8k8: b0 = B[k = t][n = g], b1 = B[k = t + 4][n = g]; k = pixel lane of the k-step, n = output column) are
+	// rebuilt inside flush_rows (a few shuffles per 16 Gaussians) instead of living in 24 registers: occupancy matters more.
+	const int fg = lane >> 2, ft = lane & 3;
+	float* sw = S.w[warp];
+	float* su = S.u[warp];
+	uint32_t nrows = 0;                                                           // warp-uniform: stashed Gaussians
+	int buf = 0;
+
+	// Pixel coordinates inside the moment product are WARP-local and centred (qx = lane%8 - 3.5, qy = lane/8 - 1.5: exact in
+	// TF32, identical for every warp), and X, Y below are relative to the same centre: the shift back from moments to
+	// sum w*dx^2 etc. then cancels as little as possible.
+	if (tid < 32)
 	{
-		const int n = min(256u, hi - b);
-		__syncthreads();
-		if (tid < n)
-		{
-			const uint32_t id = point_list[range.x + (hi - 1 - b - tid)];
-			const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
-			s_rec[3 * tid] = r0; s_rec[3 * tid + 1] = r1; s_rec[3 * tid + 2] = r2; s_id[tid] = id;
-		}
+		const float qx = (float)(tid & 7) - 3.5f, qy = (float)(tid >> 3) - 1.5f;
+		S.wgt[0 * 32 + tid] = 1.0f; S.wgt[1 * 32 + tid] = qx; S.wgt[2 * 32 + tid] = qy;
+		S.wgt[3 * 32 + tid] = qx * qx; S.wgt[4 * 32 + tid] = qx * qy; S.wgt[5 * 32 + tid] = qy * qy;
+		S.wgt[6 * 32 + tid] = 0.0f; S.wgt[7 * 32 + tid] = 0.0f;
+	}
+	S.dlp[warp][lane] = dLp0; S.dlp[warp][32 + lane] = dLp1; S.dlp[warp][64 + lane] = dLp2;
+	const float cxw = rx0 + 3.5f, cyw = ry0 + 1.5f;                                // centre of the warp's 8x4 pixel block
+	__syncthreads();
+
+	// Pixel sums of the stashed rows on the tensor cores; lane (g, t = 0) then owns rows g and g + 8: it converts the moments
+	// to the reference's sums and issues ONE set of global reductions per (warp, Gaussian) — no shared-memory accumulators,
+	// no CTA-wide flush phase, no barrier besides the one that hands over the staging buffers.
+	auto flush_rows = [&]() {
+		if (nrows == 0) return;
+		for (uint32_t r = nrows; r < 16; r++) { sw[r * STASH_LD + lane] = 0.f; su[r * STASH_LD + lane] = 0.f; }
+		__syncwarp();
+		float dw[4] = { 0.f, 0.f, 0.f, 0.f }, du[4] = { 0.f, 0.f, 0.f, 0.f };
+		const float* dl = S.dlp[warp] + (fg < 3 ? fg : 0) * 32;
 #pragma unroll
-		for (int k = 0; k < ACC_STRIDE; k++) s_acc[k * 256 + tid] = 0.0f;   // plain zero fill of the [256][9] array
-		s_touched[tid] = 0;
-		__syncthreads();
+		for (int kk = 0; kk < 4; kk++)
+		{
+			const int c0 = 8 * kk + ft, c1 = c0 + 4;
+			// B fragments: b0 = B[k = c0][n = fg], b1 = B[k = c1][n = fg]
+			const uint32_t bw0 = __float_as_uint(S.wgt[fg * 32 + c0]), bw1 = __float_as_uint(S.wgt[fg * 32 + c1]);
+			uint32_t buh0, buh1, bul0, bul1;
+			split_tf32(fg < 3 ? dl[c0] : 0.0f, buh0, bul0);
+			split_tf32(fg < 3 ? dl[c1] : 0.0f, buh1, bul1);
+			uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+			split_tf32(sw[fg * STASH_LD + c0], h0, l0); split_tf32(sw[(fg + 8) * STASH_LD + c0], h1, l1);
+			split_tf32(sw[fg * STASH_LD + c1], h2, l2); split_tf32(sw[(fg + 8) * STASH_LD + c1], h3, l3);
+			mma_tf32(dw, h0, h1, h2, h3, bw0, bw1);
+			mma_tf32(dw, l0, l1, l2, l3, bw0, bw1);
+			split_tf32(su[fg * STASH_LD + c0], h0, l0); split_tf32(su[(fg + 8) * STASH_LD + c0], h1, l1);
+			split_tf32(su[fg * STASH_LD + c1], h2, l2); split_tf32(su[(fg + 8) * STASH_LD + c1], h3, l3);
+			mma_tf32(du, h0, h1, h2, h3, buh0, buh1);
+			mma_tf32(du, l0, l1, l2, l3, buh0, buh1);
+			mma_tf32(du, h0, h1, h2, h3, bul0, bul1);
+		}
+		// D fragment: d[0] = D[g][2t], d[1] = D[g][2t+1], d[2] = D[g+8][2t], d[3] = D[g+8][2t+1]; columns of the w product:
+		// (M0 Mx | My Mxx | Mxy Myy) in lanes t = 0 | 1 | 2, of the u product (c0 c1 | c2 -) in lanes t = 0 | 1.
+		const int q1 = (lane & ~3) | 1, q2 = (lane & ~3) | 2;
+#pragma unroll
+		for (int h = 0; h < 2; h++)
+		{
+			const float My = __shfl_sync(0xffffffffu, dw[2 * h], q1), Mxx = __shfl_sync(0xffffffffu, dw[2 * h + 1], q1);
+			const float Mxy = __shfl_sync(0xffffffffu, dw[2 * h], q2), Myy = __shfl_sync(0xffffffffu, dw[2 * h + 1], q2);
+			const float c2 = __shfl_sync(0xffffffffu, du[2 * h], q1);
+			const uint32_t row = fg + 8 * h;
+			if (ft == 0 && row < nrows)
+			{
+				const float4 r0 = S.rowinfo[warp][2 * row], r1 = S.rowinfo[warp][2 * row + 1];
+				const uint32_t gid = __float_as_uint(r0.w);
+				const float X = r1.x - cxw, Y = r1.y - cyw, o = r1.z;
+				const float M0 = dw[2 * h], Mx = dw[2 * h + 1];
+				const float Sx = X * M0 - Mx, Sy = Y * M0 - My;
+				const float Sxx = X * X * M0 - 2.0f * X * Mx + Mxx;
+				const float Sxy = X * Y * M0 - X * My - Y * Mx + Mxy;
+				const float Syy = Y * Y * M0 - 2.0f * Y * My + Myy;
+				float* a = acc + 12 * (size_t)gid;
+				red_add_v4(a, du[2 * h], du[2 * h + 1], c2, M0);
+				red_add_v4(a + 4, -o * (r0.x * Sx + r0.y * Sy), -o * (r0.z * Sy + r0.y * Sx), o * Sxx, o * Sxy);
+				atomicAdd(a + 8, o * Syy);
+			}
+		}
+		__syncwarp();
+		nrows = 0;
+	};
+
+	// ---- staging pipeline: ids two batches ahead (registers), records one batch ahead (cp.async into the other buffer) ----
+	auto list_id = [&](uint32_t b) -> uint32_t {                                   // entry `tid` of the batch starting at position b (from the back)
+		const uint32_t k = b + tid;
+		return k < hi ? point_list[range.x + (hi - 1 - k)] : 0xffffffffu;
+	};
+	auto stage = [&](int to, uint32_t id) {
+		if (id != 0xffffffffu)
+		{
+			const uint32_t dst = sbase0 + (uint32_t)(to * BWD_BATCH * 3 + 3 * tid) * 16u;
+			const float4* src = rec + 3 * (size_t)id;
+			cp_async16(dst, src); cp_async16(dst + 16, src + 1); cp_async16(dst + 32, src + 2);
+			S.id[to][tid] = id;
+		}
+		cp_async_commit();
+	};
+	uint32_t id_next = 0xffffffffu;
+	if (tid < BWD_BATCH)
+	{
+		stage(0, list_id(0));
+		id_next = list_id(BWD_BATCH);
+	}
+	for (uint32_t b = 0; b < hi; b += BWD_BATCH, buf ^= 1)
+	{
+		const int n = min((uint32_t)BWD_BATCH, hi - b);
+		cp_async_wait_all();
+		__syncthreads();                                    // batch b has landed; every warp is done with the other buffer
+		if (tid < BWD_BATCH)
+		{
+			stage(buf ^ 1, id_next);
+			id_next = list_id(b + 2 * BWD_BATCH);
+		}
+		const uint32_t sbase = sbase0 + (uint32_t)(buf * BWD_BATCH * 3) * 16u;
 		for (int c0 = 0; c0 < n; c0 += 32)
 		{
 			const int j = c0 + lane;
@@ -217,27 +339,18 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 				const uint32_t addr = sbase + jj * SREC_BYTES;
 				const float4 r0 = lds128(addr), r1 = lds128(addr + 16);
 				const float dx = __fsub_rn(r1.x, pxf), dy = __fsub_rn(r1.y, pyf);
-				bool active = pos < last_contributor;                                   // backward.cu:524-526
-				float G = 0.f, alpha = 0.f;
-				if (active)
-				{
-					const float power = pair_power(r0.x, r0.y, r0.z, dx, dy);
-					active = !(power > 0.0f || power < r0.w);
-					if (active)
-					{
-						G = exp_ref(power);
-						alpha = fminf(0.99f, __fmul_rn(r1.z, G));
-						active = !(alpha < 1.0f / 255.0f);
-					}
-				}
+				const float power = pair_power(r0.x, r0.y, r0.z, dx, dy);
+				const float G = exp_ref(power);
+				const float alpha = fminf(0.99f, __fmul_rn(r1.z, G));
+				// backward.cu:524-539: same skips as the forward (pos < last_contributor replaces the `contributor` countdown)
+				const bool active = (pos < last_contributor) && !(power > 0.0f) && !(power < r0.w) && !(alpha < 1.0f / 255.0f);
 				if (!__any_sync(0xffffffffu, active)) continue;
-				float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
+				float wv = 0.f, uv = 0.f;
 				if (active)
 				{
-					const float one_m_alpha = 1.0f - alpha;
-					const float inv = __frcp_rn(one_m_alpha);
+					const float inv = __frcp_rn(1.0f - alpha);
 					T = T * inv;                                                        // backward.cu:541
-					const float dchannel_dcolor = alpha * T;
+					uv = alpha * T;
 					const float2 gb = lds64(addr + 32);
 					const float cr = r1.w, cg = gb.x, cb = gb.y;
 					const float oml = 1.0f - last_alpha;
@@ -245,34 +358,21 @@ __global__ void __launch_bounds__(256) render_backward_kernel(const uint2* __res
 					ar1 = last_alpha * lc1 + oml * ar1; lc1 = cg;
 					ar2 = last_alpha * lc2 + oml * ar2; lc2 = cb;
 					float dL_dalpha = (cr - ar0) * dLp0 + (cg - ar1) * dLp1 + (cb - ar2) * dLp2;
-					v0 = dchannel_dcolor * dLp0; v1 = dchannel_dcolor * dLp1; v2 = dchannel_dcolor * dLp2;
 					dL_dalpha *= T;
 					last_alpha = alpha;
 					dL_dalpha += (-T_final * inv) * bg_dot_dpixel;                      // backward.cu:569-572
-					const float dL_dG = r1.z * dL_dalpha;
-					const float gdx = G * dx, gdy = G * dy;
-					v3 = G * dL_dalpha;                                                 // dL_dopacity
-					v4 = dL_dG * (-gdx * r0.x - gdy * r0.y);                            // dL_dG * dG_ddelx
-					v5 = dL_dG * (-gdy * r0.z - gdx * r0.y);                            // dL_dG * dG_ddely
-					v6 = gdx * dx * dL_dG; v7 = gdx * dy * dL_dG; v8 = gdy * dy * dL_dG;
+					wv = G * dL_dalpha;
 				}
-				const float r8 = warp_reduce8(v0, v1, v2, v3, v4, v5, v6, v7, lane);
-#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
-				if ((lane & 3) == 0) atomicAdd(&s_acc[jj * ACC_STRIDE + (lane >> 2)], r8);
-				if (lane == 1) { atomicAdd(&s_acc[jj * ACC_STRIDE + 8], v8); s_touched[jj] = 1; }
+				sw[nrows * STASH_LD + lane] = wv;
+				su[nrows * STASH_LD + lane] = uv;
+				if (lane == 0) S.rowinfo[warp][2 * nrows] = make_float4(r0.x, r0.y, r0.z, __uint_as_float(S.id[buf][jj]));
+				if (lane == 1) S.rowinfo[warp][2 * nrows + 1] = r1;
+				nrows++;
+				if (nrows == 16) flush_rows();
 			}
 		}
-		__syncthreads();
-		if (tid < n && s_touched[tid])
-		{
-			float* a = acc + 12 * (size_t)s_id[tid];
-			const float* sa = s_acc + tid * ACC_STRIDE;
-			red_add_v4(a, sa[0], sa[1], sa[2], sa[3]);
-			red_add_v4(a + 4, sa[4], sa[5], sa[6], sa[7]);
-			atomicAdd(a + 8, sa[8]);
-		}
 	}
+	flush_rows();                                            // rows carry their own Gaussian data, so only the tile's tail is a partial block
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -292,8 +392,10 @@ int launch_render_backward(const ImageState& img, const BinningState& b, const G
 	const float* dL_dpix, float* acc, cudaStream_t stream)
 {
 	const dim3 grid((W + GSB_TILE_X - 1) / GSB_TILE_X, (H + GSB_TILE_Y - 1) / GSB_TILE_Y);
+	static bool attr_set = false;
+	if (!attr_set) { GSB_CUDA_OK(cudaFuncSetAttribute(render_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem))); attr_set = true; }
 	ProfScope prof(K_RENDER_BWD, stream);
-	render_backward_kernel<<<grid, 256, 0, stream>>>(img.ranges, b.point_list, W, H, g.rec, bg,
+	render_backward_kernel<<<grid, 256, sizeof(BwdSmem), stream>>>(img.ranges, b.point_list, W, H, g.rec, bg,
 		img.final_T, img.n_contrib, img.tile_max_contrib, dL_dpix, acc);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
