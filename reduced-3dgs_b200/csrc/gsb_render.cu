@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 // m16n8k8 MMAs (fp32-level accuracy: operands are split hi/lo, the per-pixel weights 1, px, py, px^2, px*py, py^2 are exact in
 // TF32), instead of a 14-shuffle butterfly + 9 products per (warp, Gaussian).  tcgen05 is not applicable to a per-warp
 // 16x32x8 product (it needs 64/128-row tiles from shared-memory descriptors and TMEM); this is the warp-level MMA path.
-#define BWD_BATCH 96
+#define BWD_BATCH 64
 #define STASH_LD 36            // row stride of the (w, u) stash: conflict-free A-fragment loads
 #define ACC_STRIDE 9           // per staged Gaussian: [dcol0 dcol1 dcol2 M0 Mx My Mxx Mxy Myy]
 
@@ -166,9 +166,12 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+#define BWD_STAGES 3
 struct BwdSmem {
-	float4 rec[2][BWD_BATCH * 3];          // double-buffered staging of the tile's list (cp.async gather, one batch ahead)
-	uint32_t id[2][BWD_BATCH];
+	float4 rec[BWD_STAGES][BWD_BATCH * 3]; // ring of staged batches of the tile's list: one 48-byte TMA bulk copy per instance
+	uint32_t id[BWD_STAGES][BWD_BATCH];
+	uint64_t full[BWD_STAGES];             // mbarrier: the stage's copies have landed (96 arrivals + transaction bytes)
+	uint64_t empty[BWD_STAGES];            // mbarrier: all 8 warps are done reading the stage
 	float w[8][16 * STASH_LD];
 	float u[8][16 * STASH_LD];
 	float4 rowinfo[8][16 * 2];            // per stashed row: (conic.xyz, id bits), (mean2D.xy, opacity, -): rows outlive their staging buffer
@@ -290,37 +293,49 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 		nrows = 0;
 	};
 
-	// ---- staging pipeline: ids two batches ahead (registers), records one batch ahead (cp.async into the other buffer) ----
-	auto list_id = [&](uint32_t b) -> uint32_t {                                   // entry `tid` of the batch starting at position b (from the back)
-		const uint32_t k = b + tid;
-		return k < hi ? point_list[range.x + (hi - 1 - k)] : 0xffffffffu;
+	// ---- staging ring: warps do NOT run in lockstep.  A batch of 96 list entries is gathered by 96 threads, one 48-byte TMA
+	// bulk copy (cp.async.bulk, completion by mbarrier transaction bytes) per entry, BWD_STAGES - 1 batches ahead of the
+	// slowest warp; a warp that finishes a batch early moves on to the next stage instead of waiting at a CTA barrier.
+	auto list_id = [&](uint32_t bi) -> uint32_t {                                  // entry `tid` of batch bi (counted from the back of the list)
+		const uint32_t k = bi * BWD_BATCH + tid;
+		return (tid < BWD_BATCH && k < hi) ? point_list[range.x + (hi - 1 - k)] : 0xffffffffu;
 	};
-	auto stage = [&](int to, uint32_t id) {
+	auto issue = [&](uint32_t bi, uint32_t id) {                                   // threads tid < BWD_BATCH
+		const int st = bi % BWD_STAGES;
 		if (id != 0xffffffffu)
 		{
-			const uint32_t dst = sbase0 + (uint32_t)(to * BWD_BATCH * 3 + 3 * tid) * 16u;
-			const float4* src = rec + 3 * (size_t)id;
-			cp_async16(dst, src); cp_async16(dst + 16, src + 1); cp_async16(dst + 32, src + 2);
-			S.id[to][tid] = id;
+			S.id[st][tid] = id;
+			mbar_arrive_expect_tx(&S.full[st], 48u);
+			tma_bulk_g2s(&S.rec[st][3 * tid], rec + 3 * (size_t)id, 48u, &S.full[st]);
 		}
-		cp_async_commit();
+		else mbar_arrive(&S.full[st]);
 	};
+	const uint32_t nb = (hi + BWD_BATCH - 1) / BWD_BATCH;
+	if (tid == 0)
+	{
+		for (int k = 0; k < BWD_STAGES; k++) { mbar_init(&S.full[k], BWD_BATCH); mbar_init(&S.empty[k], 8); }
+		mbar_fence_init();
+	}
+	__syncthreads();
 	uint32_t id_next = 0xffffffffu;
 	if (tid < BWD_BATCH)
 	{
-		stage(0, list_id(0));
-		id_next = list_id(BWD_BATCH);
+		for (uint32_t k = 0; k < BWD_STAGES - 1 && k < nb; k++) issue(k, list_id(k));
+		id_next = list_id(BWD_STAGES - 1);
 	}
-	for (uint32_t b = 0; b < hi; b += BWD_BATCH, buf ^= 1)
+	for (uint32_t bi = 0; bi < nb; bi++)
 	{
+		const uint32_t b = bi * BWD_BATCH;
 		const int n = min((uint32_t)BWD_BATCH, hi - b);
-		cp_async_wait_all();
-		__syncthreads();                                    // batch b has landed; every warp is done with the other buffer
-		if (tid < BWD_BATCH)
+		buf = bi % BWD_STAGES;
+		if (tid < BWD_BATCH && bi + BWD_STAGES - 1 < nb)
 		{
-			stage(buf ^ 1, id_next);
-			id_next = list_id(b + 2 * BWD_BATCH);
+			// the stage that batch bi + STAGES - 1 goes into was last read for batch bi - 1
+			if (bi >= 1) mbar_wait(&S.empty[(bi - 1) % BWD_STAGES], ((bi - 1) / BWD_STAGES) & 1u);
+			issue(bi + BWD_STAGES - 1, id_next);
+			id_next = list_id(bi + BWD_STAGES);
 		}
+		mbar_wait(&S.full[buf], (bi / BWD_STAGES) & 1u);
 		const uint32_t sbase = sbase0 + (uint32_t)(buf * BWD_BATCH * 3) * 16u;
 		for (int c0 = 0; c0 < n; c0 += 32)
 		{
@@ -371,8 +386,10 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 				if (nrows == 16) flush_rows();
 			}
 		}
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&S.empty[buf]);           // this warp no longer reads the stage (stashed rows carry their own data)
 	}
-	flush_rows();                                            // rows carry their own Gaussian data, so only the tile's tail is a partial block
+	flush_rows();                                            // only the tile's tail is a partial block
 }
 
 // ------------------------------------------------------------------------------------------------
