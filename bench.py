@@ -261,6 +261,8 @@ def main():
     # warm-up runs the SAME loop body as the timed region (L2 flush, event pair, step) so that every lazily initialised piece
     # (kernel modules, caching-allocator blocks for each view's sizes, event pools) exists before timing starts
     n_warm = max(Wm, 8)
+    if args.impl == "ours":
+        gsl.profile_enable(True)                 # per-kernel event pairs are part of the measured configuration: warm them up too
     for i in range(n_warm):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -270,8 +272,7 @@ def main():
     R0, color0, radii0, ib0, _ = out
     torch.cuda.synchronize()
     if args.impl == "ours":
-        gsl.profile_enable(True)
-        gsl.profile_read()
+        gsl.profile_read()                       # discard warm-up samples (recycles the events)
         launches0 = gsl.launch_count()
     sampler = ClockSampler(physical_gpu_index(local))
     barrier()
@@ -317,6 +318,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return 0
 
     # ---------------- roofline of the dominant kernel ----------------
@@ -381,9 +383,10 @@ def main():
                                 "sample": "the reference's own implementation of this path is CUDA (no CPU rasterizer exists): "
                                           "oracle/_ref/_refC.so = unmodified reference sources + GLM stand-in, timed on the same B200, "
                                           "debug syncs off (the faster of the two ways the reference can run)"}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1 and args.impl == "ours":
         dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -51,10 +51,10 @@ static const char* kKernelNames[K_COUNT] = { "preprocess", "tile_scan", "scatter
 	"render_forward", "render_backward", "preprocess_backward", "mark_visible" };
 
 int launch_debug_dequant(const GsbQuant*, int, float*, float*, cudaStream_t);
-int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, uint32_t*, int32_t*, const GsbDebug*, cudaStream_t);
+int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, const ImageState&, const BinPlan&, int32_t*, const GsbDebug*, cudaStream_t);
 int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
-int launch_tile_scan(const ImageState&, const GeomState&, int, int, cudaStream_t);
-int launch_binning(const GeomState&, const BinningState&, const ImageState&, int, long long, int, int, cudaStream_t);
+int launch_tile_scan(const ImageState&, const GeomState&, const BinPlan&, int, int, cudaStream_t);
+int launch_binning(const GeomState&, const BinningState&, const ImageState&, const BinPlan&, int, long long, int, int, cudaStream_t);
 int launch_export_binning(const GeomState&, const BinningState&, const ImageState&, int, int, uint64_t*, uint32_t*, cudaStream_t);
 int launch_render_forward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, float*, cudaStream_t);
 int launch_render_backward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, const float*, float*, cudaStream_t);
@@ -96,7 +96,8 @@ using namespace gsb;
 extern "C" {
 
 size_t gsb_geom_bytes(int32_t P) { return geom_state_bytes(P) + size_t(P) * 48 + 512; }
-size_t gsb_image_bytes(int32_t W, int32_t H) { size_t b; ImageState::carve(nullptr, W, H, &b); return b + 256; }
+// the image blob is sized for the largest per-CTA histogram table the forward can ask for (592 CTAs)
+size_t gsb_image_bytes(int32_t W, int32_t H) { size_t b; ImageState::carve(nullptr, W, H, &b, 148 * 4); return b + 256; }
 size_t gsb_binning_bytes(int64_t R) { size_t b; BinningState::carve(nullptr, R, &b); return b + 256; }
 uint64_t gsb_launch_count(void) { return g_launch_count; }
 const char* gsb_last_error(void) { return g_err; }
@@ -146,11 +147,12 @@ int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_a
 	char* img_blob = image_alloc(image_user, gsb_image_bytes(W, H));
 	if (!geom_blob || !img_blob) { set_error("scratch allocation failed"); return GSB_ENOMEM; }
 	GeomState g = GeomState::carve(geom_blob, P);
-	ImageState img = ImageState::carve(img_blob, W, H);
+	const BinPlan plan = make_bin_plan(P, W, H, scene->quant != nullptr);
+	ImageState img = ImageState::carve(img_blob, W, H, nullptr, plan.priv ? plan.ctas : 0);
 	GSB_CUDA_OK(cudaMemsetAsync(g.counters, 0, 16 * sizeof(uint32_t), stream));
-	GSB_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, ImageState::tiles(W, H) * sizeof(uint32_t), stream));
-	if (int e = launch_preprocess(scene, cam, g, img.tile_count, radii, debug, stream)) return e;
-	if (int e = launch_tile_scan(img, g, W, H, stream)) return e;
+	if (!plan.priv) GSB_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, ImageState::tiles(W, H) * sizeof(uint32_t), stream));
+	if (int e = launch_preprocess(scene, cam, g, img, plan, radii, debug, stream)) return e;
+	if (int e = launch_tile_scan(img, g, plan, W, H, stream)) return e;
 	// the instance count sizes the binning blob (rasterizer_impl.cu:445-450): one 16-byte read-back
 	static thread_local uint32_t* h_counters = nullptr;
 	if (!h_counters) GSB_CUDA_OK(cudaMallocHost(&h_counters, 16 * sizeof(uint32_t)));
@@ -163,7 +165,7 @@ int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_a
 	char* bin_blob = binning_alloc(binning_user, gsb_binning_bytes(R));
 	if (!bin_blob) { set_error("binning allocation failed"); return GSB_ENOMEM; }
 	BinningState b = BinningState::carve(bin_blob, R);
-	if (int e = launch_binning(g, b, img, P, R, W, H, stream)) return e;
+	if (int e = launch_binning(g, b, img, plan, P, R, W, H, stream)) return e;
 	if (int e = launch_render_forward(img, b, g, W, H, cam->background, out_color, stream)) return e;
 	return GSB_OK;
 }

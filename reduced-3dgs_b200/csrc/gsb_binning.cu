@@ -64,6 +64,71 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 	if (tid == 0) counters[0] = s_carry;            // num_rendered
 }
 
+// Per tile: turn the per-CTA histograms into exclusive prefixes over CTAs (in place) and emit the tile total.
+// CTA = 32 tiles x 8 CTA-groups: lanes of a warp read 32 consecutive tiles of one histogram row (128-byte segments), each
+// warp scans its own eighth of the rows, the eight partial totals are combined through shared memory.
+__global__ void __launch_bounds__(256) tile_prefix_kernel(uint32_t* __restrict__ cta_count, int ctas, int T, uint32_t* __restrict__ tile_count)
+{
+	__shared__ uint32_t s_part[8][32];
+	const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+	const int t = blockIdx.x * 32 + lane;
+	const int per = (ctas + 7) / 8, c0 = grp * per, c1 = min(ctas, c0 + per);
+	uint32_t run = 0;
+	if (t < T)
+		for (int c = c0; c < c1; c++) { const uint32_t v = cta_count[(size_t)c * T + t]; cta_count[(size_t)c * T + t] = run; run += v; }
+	s_part[grp][lane] = run;
+	__syncthreads();
+	uint32_t off = 0, total = 0;
+#pragma unroll
+	for (int g = 0; g < 8; g++) { const uint32_t v = s_part[g][lane]; if (g < grp) off += v; total += v; }
+	if (t < T)
+	{
+		if (off) for (int c = c0; c < c1; c++) cta_count[(size_t)c * T + t] += off;
+		if (grp == 0) tile_count[t] = total;
+	}
+}
+
+// Scatter with privatised cursors: CTA c (same Gaussian chunk as in the preprocess kernel) starts every tile's cursor at
+// tile start + (instances of that tile owned by CTAs < c); slots are then claimed with shared-memory atomics only.
+__global__ void __launch_bounds__(256) scatter_priv_kernel(int P, int chunk, int T, const float4* __restrict__ rec, const uint2* __restrict__ rect,
+	const uint2* __restrict__ ranges, const uint32_t* __restrict__ cta_base, int gx, uint64_t* __restrict__ bucket)
+{
+	extern __shared__ uint32_t s_cur[];
+	const uint32_t* base = cta_base + (size_t)blockIdx.x * T;
+	for (int t = threadIdx.x; t < T; t += blockDim.x) s_cur[t] = ranges[t].x + base[t];
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const long long first = (long long)blockIdx.x * chunk, last = min((long long)P, first + chunk);
+	for (long long b0 = first; b0 < last; b0 += blockDim.x)
+	{
+		const long long idx = b0 + threadIdx.x;
+		uint2 rc = make_uint2(0, 0); uint32_t dbits = 0;
+		if (idx < last)
+		{
+			rc = rect[idx];
+			if (rc.x | rc.y) dbits = __float_as_uint(rec[3 * (size_t)idx + 2].z);
+		}
+		const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16, miny = rc.y & 0xffffu, maxy = rc.y >> 16;
+		const uint32_t w = maxx - minx, t = w * (maxy - miny);
+		const bool big = t > 32;
+		if (t && !big)
+		{
+			const uint64_t comp = ((uint64_t)dbits << 32) | (uint32_t)idx;
+			for (uint32_t y = miny; y < maxy; y++)
+				for (uint32_t x = minx; x < maxx; x++) bucket[atomicAdd(&s_cur[y * gx + x], 1u)] = comp;
+		}
+		unsigned bigmask = __ballot_sync(0xffffffffu, big);
+		while (bigmask)
+		{
+			const int src = __ffs(bigmask) - 1; bigmask &= bigmask - 1;
+			const uint32_t bt = __shfl_sync(0xffffffffu, t, src), bw = __shfl_sync(0xffffffffu, w, src);
+			const uint32_t bminx = __shfl_sync(0xffffffffu, minx, src), bminy = __shfl_sync(0xffffffffu, miny, src);
+			const uint64_t comp = ((uint64_t)__shfl_sync(0xffffffffu, dbits, src) << 32) | (uint32_t)(idx - lane + src);
+			for (uint32_t k = lane; k < bt; k += 32) bucket[atomicAdd(&s_cur[(bminy + k / bw) * gx + bminx + k % bw], 1u)] = comp;
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // One thread per Gaussian writes its instances; Gaussians covering more than 32 tiles are handled by the whole warp.
 __global__ void __launch_bounds__(256) scatter_kernel(int P, const float4* __restrict__ rec, const uint2* __restrict__ rect,
@@ -395,24 +460,36 @@ __global__ void __launch_bounds__(1024) tile_sort_big_kernel(const uint2* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-int launch_tile_scan(const ImageState& img, const GeomState& g, int W, int H, cudaStream_t stream)
+int launch_tile_scan(const ImageState& img, const GeomState& g, const BinPlan& plan, int W, int H, cudaStream_t stream)
 {
 	const int T = ((W + GSB_TILE_X - 1) / GSB_TILE_X) * ((H + GSB_TILE_Y - 1) / GSB_TILE_Y);
 	ProfScope prof(K_SCAN, stream);
+	if (plan.priv)
+	{
+		tile_prefix_kernel<<<(T + 31) / 32, 256, 0, stream>>>(img.cta_count, plan.ctas, T, img.tile_count);
+		GSB_LAUNCHED();
+	}
 	tile_scan_kernel<<<1, 1024, 0, stream>>>(img.tile_count, T, img.ranges, g.counters, img.tile_cursor, img.cls_list, img.cls_count);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
 	return GSB_OK;
 }
 
-int launch_binning(const GeomState& g, const BinningState& b, const ImageState& img, int P, long long R, int W, int H, cudaStream_t stream)
+int launch_binning(const GeomState& g, const BinningState& b, const ImageState& img, const BinPlan& plan, int P, long long R, int W, int H, cudaStream_t stream)
 {
 	if (R == 0) return GSB_OK;
 	const int gx = (W + GSB_TILE_X - 1) / GSB_TILE_X, gy = (H + GSB_TILE_Y - 1) / GSB_TILE_Y;
 	const int T = gx * gy;
 	{
 		ProfScope prof(K_EMIT_KEYS, stream);
-		scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, img.ranges, img.tile_cursor, gx, b.bucket);
+		if (plan.priv)
+		{
+			static bool attr = false;
+			if (!attr) { GSB_CUDA_OK(cudaFuncSetAttribute(scatter_priv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); attr = true; }
+			scatter_priv_kernel<<<plan.ctas, 256, plan.hist_bytes, stream>>>(P, plan.chunk, T, g.rec, g.rect, img.ranges, img.cta_count, gx, b.bucket);
+		}
+		else
+			scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, img.ranges, img.tile_cursor, gx, b.bucket);
 		GSB_LAUNCHED();
 	}
 	constexpr size_t smemA = size_t(GSB_SORT_CAP_A) * 16 + 8 * 256 * 4, smemB = size_t(GSB_SORT_CAP_B) * 16 + 32 * 256 * 4;

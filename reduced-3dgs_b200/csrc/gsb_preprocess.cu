@@ -19,6 +19,7 @@ struct PreArgs {
 	const uint8_t* prune;
 	int quant; GsbQuant q;
 	GeomState g; int32_t* radii; uint32_t* tile_count;
+	int hist_priv, chunk, T; uint32_t* cta_count;      // privatised tile counting (gsb_common.cuh BinPlan)
 	GsbDebug dbg; int prefiltered;
 };
 
@@ -97,13 +98,23 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 		}
 		__syncthreads();
 	}
+	uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_cb + (QUANT ? GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE : 0));
+	if (a.hist_priv)
+	{
+		for (int t = threadIdx.x; t < a.T; t += blockDim.x) s_hist[t] = 0;
+		__syncthreads();
+	}
 	unsigned block_vis = 0;
-	for (long long base = (long long)blockIdx.x * blockDim.x; base < a.P; base += (long long)gridDim.x * blockDim.x)
+	// privatised counting: CTA c owns the contiguous Gaussians [c*chunk, (c+1)*chunk) (the scatter kernel uses the same map)
+	const long long first = a.hist_priv ? (long long)blockIdx.x * a.chunk : (long long)blockIdx.x * blockDim.x;
+	const long long last = a.hist_priv ? min((long long)a.P, first + a.chunk) : (long long)a.P;
+	const long long stride = a.hist_priv ? (long long)blockDim.x : (long long)gridDim.x * blockDim.x;
+	for (long long base = first; base < last; base += stride)
 	{
 		const long long idx = base + threadIdx.x;
 		bool visible = false;
 		uint32_t my_tiles = 0; uint2 my_rect = make_uint2(0, 0);
-		if (idx < a.P)
+		if (idx < last)
 		{
 			uint32_t tiles = 0; int radius_i = 0;
 			uint2 rect = make_uint2(0, 0);
@@ -239,20 +250,33 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
 			const bool big = my_tiles > 32;
 			if (my_tiles && !big)
 				for (uint32_t y = miny; y < maxy; y++)
-					for (uint32_t x = minx; x < maxx; x++) atomicAdd(&a.tile_count[y * a.gx + x], 1u);
+					for (uint32_t x = minx; x < maxx; x++)
+					{
+						if (a.hist_priv) atomicAdd(&s_hist[y * a.gx + x], 1u); else atomicAdd(&a.tile_count[y * a.gx + x], 1u);
+					}
 			unsigned bigmask = __ballot_sync(0xffffffffu, big);
 			while (bigmask)
 			{
 				const int src = __ffs(bigmask) - 1; bigmask &= bigmask - 1;
 				const uint32_t bt = __shfl_sync(0xffffffffu, my_tiles, src), bw = __shfl_sync(0xffffffffu, w, src);
 				const uint32_t bminx = __shfl_sync(0xffffffffu, minx, src), bminy = __shfl_sync(0xffffffffu, miny, src);
-				for (uint32_t k = threadIdx.x & 31; k < bt; k += 32) atomicAdd(&a.tile_count[(bminy + k / bw) * a.gx + bminx + k % bw], 1u);
+				for (uint32_t k = threadIdx.x & 31; k < bt; k += 32)
+				{
+					const uint32_t t = (bminy + k / bw) * a.gx + bminx + k % bw;
+					if (a.hist_priv) atomicAdd(&s_hist[t], 1u); else atomicAdd(&a.tile_count[t], 1u);
+				}
 			}
 		}
 		block_vis += __popc(__ballot_sync(0xffffffffu, visible)) * ((threadIdx.x & 31) == 0);
 	}
 	// number of visible Gaussians (SH-sparsity multiplier, rasterizer_impl.cu:549-571) without a later reduction pass
 	if ((threadIdx.x & 31) == 0 && block_vis) atomicAdd(&a.g.counters[1], block_vis);
+	if (a.hist_priv)
+	{
+		__syncthreads();
+		uint32_t* dst = a.cta_count + (size_t)blockIdx.x * a.T;
+		for (int t = threadIdx.x; t < a.T; t += blockDim.x) dst[t] = s_hist[t];
+	}
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view, uint8_t* __restrict__ present)
@@ -284,7 +308,7 @@ int launch_debug_dequant(const GsbQuant* q, int P, float* scales, float* rots, c
 	return GSB_OK;
 }
 
-int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& g, uint32_t* tile_count, int32_t* radii, const GsbDebug* dbg, cudaStream_t stream)
+int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& g, const ImageState& img, const BinPlan& plan, int32_t* radii, const GsbDebug* dbg, cudaStream_t stream)
 {
 	PreArgs a{};
 	a.P = s->P; a.M = s->M; a.W = cam->width; a.H = cam->height;
@@ -310,19 +334,24 @@ int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& 
 	a.prune = s->prune_mask;
 	a.quant = s->quant != nullptr;
 	if (s->quant) a.q = *s->quant;
-	a.g = g; a.radii = radii; a.tile_count = tile_count;
+	a.g = g; a.radii = radii; a.tile_count = img.tile_count;
+	a.hist_priv = plan.priv; a.chunk = plan.chunk; a.T = a.gx * a.gy; a.cta_count = img.cta_count;
 	if (dbg) a.dbg = *dbg;
 	a.prefiltered = cam->prefiltered;
 	const int blocks_needed = (s->P + 255) / 256;
-	ProfScope prof(K_PREPROCESS, stream);
-	if (a.quant)
+	const size_t smem = (a.quant ? GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE * sizeof(float) : 0) + (plan.priv ? plan.hist_bytes : 0);
+	static bool attr_set = false;
+	if (!attr_set)
 	{
-		const int smem = GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE * sizeof(float);
-		const int grid = blocks_needed < 148 * 8 ? blocks_needed : 148 * 8;               // persistent: amortise the table load
-		preprocess_kernel<true><<<grid, 256, smem, stream>>>(a);
+		GSB_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+		GSB_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+		attr_set = true;
 	}
-	else
-		preprocess_kernel<false><<<blocks_needed, 256, 0, stream>>>(a);
+	ProfScope prof(K_PREPROCESS, stream);
+	int grid = plan.priv ? plan.ctas : blocks_needed;
+	if (!plan.priv && a.quant && grid > 148 * 8) grid = 148 * 8;                         // persistent: amortise the table load
+	if (a.quant) preprocess_kernel<true><<<grid, 256, smem, stream>>>(a);
+	else preprocess_kernel<false><<<grid, 256, smem, stream>>>(a);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
 	return GSB_OK;
