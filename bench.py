@@ -278,6 +278,9 @@ def main():
     barrier()
     if rank == 0 and not os.environ.get("GS_BENCH_NO_CLOCKS"):
         sampler.start()
+    import gc
+    gc.collect()
+    gc.disable()                                  # a cyclic-GC pause between two launches would show up as GPU idle time
     evs = []
     for i in range(K):
         flush.zero_()
@@ -295,6 +298,7 @@ def main():
         torch.cuda.synchronize()
         coll_ms = e0.elapsed_time(e1)
     barrier()
+    gc.enable()
     clocks = (sampler.stop() if sampler._thread is not None or sampler.nv is None else {"sm_mhz": None, "reasons": ["sampling disabled"]}) if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(step_ms) + coll_ms
@@ -438,6 +442,9 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
     if world > 1 and args.impl == "ours":
         dist.barrier()
     ms = 0.0
+    import gc
+    gc.collect()
+    gc.disable()
     for i in range(K):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -446,6 +453,7 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
         e1.record()
         torch.cuda.synchronize()
         ms += e0.elapsed_time(e1)
+    gc.enable()
     if world > 1 and args.impl == "ours":
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 	const float pxf = (float)px, pyf = (float)py;
 	const float rx0 = (float)wx0, rx1 = (float)(wx0 + 7), ry0 = (float)wy0, ry1 = (float)(wy0 + 3);
 	const uint2 range = ranges[tile];
-	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_rec);
+	uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_rec);
+	asm volatile("" : "+r"(sbase));                       // keep the shared-window address in a register (otherwise re-derived from SR_CgaCtaId every iteration)
 	if (tid == 0) s_max = 0;
 
 	bool done = !inside;
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 	const float rx0 = (float)(tx0 + (warp & 1) * 8), rx1 = rx0 + 7.0f, ry0 = (float)(ty0 + (warp >> 1) * 4), ry1 = ry0 + 3.0f;
 	const uint2 range = ranges[tile];
 	const size_t pid = (size_t)W * py + px, N = (size_t)W * H;
-	const uint32_t sbase0 = (uint32_t)__cvta_generic_to_shared(&S.rec[0][0]);
+	uint32_t sbase0 = (uint32_t)__cvta_generic_to_shared(&S.rec[0][0]);
+	asm volatile("" : "+r"(sbase0));
 
 	const float T_final = inside ? final_Ts[pid] : 0.0f;
 	float T = T_final;
