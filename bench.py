@@ -372,13 +372,22 @@ def main():
         ach = B[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
         frame_bytes = sum(B.values())
         kern_ms = sum(stage_ms.values())
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this config (profiles/traffic.json,
+        # written by tools/ncu_summary.py); null when this config / kernel has no capture
+        traffic = None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+        if os.path.isfile(tpath) and not args.points:
+            traffic = json.load(open(tpath)).get(name, {}).get(dom)
+        fwd_ms = stage_ms["preprocess"] + stage_ms["binning"] + stage_ms["render_forward"]
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes": int(B[dom]), "kernel_ms": round(stage_ms[dom], 4),
+                "frac": round(ach / peak, 4), "traffic": traffic, "algorithmic_bytes": int(B[dom]), "kernel_ms": round(stage_ms[dom], 4),
                 "stages": {g: {"ms": round(stage_ms[g], 4), "alg_MB": round(B[g] / 1e6, 1),
                                "GBps": round(B[g] / max(stage_ms[g], 1e-9) / 1e6, 1),
                                "frac": round(B[g] / max(stage_ms[g], 1e-9) / 1e6 / peak, 4)} for g in groups},
                 "frame": {"alg_MB": round(frame_bytes / 1e6, 1), "kernel_ms": round(kern_ms, 4),
                           "frac": round(frame_bytes / max(kern_ms, 1e-9) / 1e6 / peak, 4)},
+                "fwd_only": {"kernel_ms": round(fwd_ms, 4), "Mpix_s": round(Npx / max(fwd_ms, 1e-9) / 1e3, 1),
+                             "note": "sum of the forward kernels' device time (preprocess + binning + render_forward)"},
                 "rho_list_consumed": round(rho, 4), "kernels": per_kernel}
 
     # ---------------- CPU baseline: the oracle on the host cores, one view of the same workload ----------------

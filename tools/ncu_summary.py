@@ -32,7 +32,33 @@ def main(rep, out):
         for r in rows[2:]:
             w.writerow([r[i][:70] if n == "kernel" else r[i] for i, n in idx])
     print("wrote", out, len(rows) - 2, "kernels")
+    return rows
+
+
+def traffic(rows):
+    """{kernel id: dram bytes read+written per launch} — feeds bench.py's roofline.traffic (profiles/traffic.json)."""
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ids = [("render_forward", "render_forward"), ("render_backward", "render_backward"), ("preprocess_backward", "preprocess_backward"),
+           ("preprocess_kernel", "preprocess"), ("scatter", "scatter"), ("tile_sort_dist", "tile_sort"), ("tile_prefix", "tile_prefix"),
+           ("tile_scan", "tile_scan")]
+    out = {}
+    for r in rows[2:]:
+        for pat, kid in ids:
+            if pat in r[ki]:
+                b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+                out[kid] = int(b)
+                break
+    return out
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    rows = main(sys.argv[1], sys.argv[2])
+    if len(sys.argv) > 4:          # ... <traffic.json> <config key>: merge this capture's DRAM traffic per launch
+        import json, os
+        path, key = sys.argv[3], sys.argv[4]
+        d = json.load(open(path)) if os.path.isfile(path) else {}
+        d[key] = traffic(rows)
+        json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+        print("updated", path, key, d[key])
