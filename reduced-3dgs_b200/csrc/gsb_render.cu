@@ -11,8 +11,9 @@
 // final_T and colours are unchanged.  The per-pixel arithmetic is the reference's, operation for operation.
 //
 // Backward: instead of 9 global atomicAdds per contributing (pixel, Gaussian) pair (backward.cu:561-592) the 9
-// partial gradients are reduced across the warp with a transposed butterfly (14 shuffles), combined across the
-// 8 warps in shared memory and flushed once per (tile, Gaussian) with two vector reductions + one scalar.
+// per-Gaussian sums over a warp's 32 pixels are computed as a small matrix product on the tensor cores (3xTF32
+// mma.sync, see below) and added to the per-Gaussian accumulator with three vector reductions per (warp, Gaussian).
+// The tile's list is staged through a ring of shared-memory buffers filled by TMA bulk copies (mbarrier-tracked).
 #include "gsb_common.cuh"
 
 namespace gsb {
