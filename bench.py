@@ -63,56 +63,49 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region through NVML (pynvml) from a thread.
-    (Polling with the nvidia-smi binary perturbs the run: each query stalls kernel launches for milliseconds.)"""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (pynvml), from the main thread in the gap
+    between two steps (after the L2 flush is launched, before the next step's start event is recorded).
+    Two earlier designs perturbed the measurement and were dropped: polling with the nvidia-smi binary stalled kernel launches
+    for milliseconds per query, and an NVML polling thread occasionally held a driver lock across a step's launches
+    (one step in a few hundred took 30-100 ms)."""
 
-    def __init__(self, index):
-        self.index, self.sm, self.reasons, self.max_sm = index, [], set(), None
-        self._stop = threading.Event()
-        self._thread = None
+    def __init__(self, index, enabled=True):
+        self.index, self.sm, self.reasons, self.max_sm, self.nv = index, [], set(), None, None
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
-            self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            # the FIRST call of each NVML query initialises driver state under a lock that blocks CUDA calls of other threads
-            # for 20-200 ms: make those first calls here, long before the timed region
-            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.nv = pynvml
+            self.names = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                          "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                          "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                          "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            self.sample(keep=False)                  # the first call of each query initialises driver state (20-200 ms)
         except Exception:
             self.nv = None
-        self.armed = False
 
-    def _poll(self):
-        nv = self.nv
-        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-        while not self._stop.is_set():
-            try:
-                c = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                if self.armed:                       # polling starts during warm-up; only samples inside the timed region count
-                    self.sm.append(c)
-                    for n, bit in names.items():
-                        if r & bit:
-                            self.reasons.add(n)
-            except Exception:
-                pass
-            self._stop.wait(0.02)
-
-    def start(self):
-        if self.nv is not None:
-            self._thread = threading.Thread(target=self._poll, daemon=True)
-            self._thread.start()
-
-    def stop(self):
+    def sample(self, keep=True):
         if self.nv is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
-        self._stop.set()
-        self._thread.join(timeout=1.0)
+            return
+        try:
+            c = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        except Exception:
+            return
+        if keep:
+            self.sm.append(c)
+            for n, bit in self.names.items():
+                if r & bit:
+                    self.reasons.add(n)
+
+    def result(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable or sampling disabled"]}
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
-                "samples": len(self.sm)}
+                "samples": len(self.sm), "where": "main thread, between steps of the timed region (GPU busy with the L2 flush)"}
 
 
 def physical_gpu_index(local: int) -> int:
@@ -267,14 +260,13 @@ def main():
     # ---------------- device-resident measurement (`value`) ----------------
     # warm-up runs the SAME loop body as the timed region (L2 flush, event pair, step) so that every lazily initialised piece
     # (kernel modules, caching-allocator blocks for each view's sizes, event pools) exists before timing starts
-    n_warm = max(Wm, 8)
-    sampler = ClockSampler(physical_gpu_index(local))
-    if rank == 0 and not os.environ.get("GS_BENCH_NO_CLOCKS"):
-        sampler.start()                          # polls through the warm-up; samples are kept only once armed
+    n_warm = max(Wm, 12)
+    sampler = ClockSampler(physical_gpu_index(local), enabled=(rank == 0 and not os.environ.get("GS_BENCH_NO_CLOCKS")))
     if args.impl == "ours":
         gsl.profile_enable(True)                 # per-kernel event pairs are part of the measured configuration: warm them up too
     for i in range(n_warm):
         flush.zero_()
+        sampler.sample(keep=False)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = step(i, G)
@@ -286,16 +278,16 @@ def main():
     if args.impl == "ours":
         gsl.profile_read()                       # discard warm-up samples (recycles the events)
         launches0 = gsl.launch_count()
-    barrier()
-    sampler.armed = True
     import gc
     gc.collect()
     gc.disable()                                  # a cyclic-GC pause between two launches would show up as GPU idle time
     ms0 = torch.cuda.memory_stats(dev)
+    barrier()
     host_t = []
     evs = []
     for i in range(K):
         flush.zero_()
+        sampler.sample()                         # in the gap: the step's launches below never overlap an NVML call
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t_h = time.perf_counter()
@@ -318,7 +310,7 @@ def main():
     barrier()
     gc.enable()
     R0, color0, radii0, ib0, _ = out             # (taken after the loop: holding a warm-up generation would grow the live set mid-run)
-    clocks = (sampler.stop() if sampler._thread is not None or sampler.nv is None else {"sm_mhz": None, "reasons": ["sampling disabled"]}) if rank == 0 else None
+    clocks = sampler.result() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
     if os.environ.get("GS_BENCH_DEBUG"):
         ms1 = torch.cuda.memory_stats(dev)

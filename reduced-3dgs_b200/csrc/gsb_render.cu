@@ -161,6 +161,12 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo)
 // acc record written for the preprocess backward (12 floats per Gaussian, 48 B): [dcol.r dcol.g dcol.b dop | sx sy cxx cxy | cyy - - -]
 // sx = sum dL_dG*dG_ddelx, sy = sum dL_dG*dG_ddely, cxx = sum gdx*dx*dL_dG, cxy = sum gdx*dy*dL_dG, cyy = sum gdy*dy*dL_dG;
 // the constant factors (0.5*W, 0.5*H, -0.5) of backward.cu:583-589 are applied once per Gaussian by the consumer.
+__device__ __forceinline__ float rcp_approx(float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr)
 {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -168,7 +174,7 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-#define BWD_STAGES 3
+#define BWD_STAGES 4
 struct BwdSmem {
 	float4 rec[BWD_STAGES][BWD_BATCH * 3]; // ring of staged batches of the tile's list: one 48-byte TMA bulk copy per instance
 	uint32_t id[BWD_STAGES][BWD_BATCH];
@@ -176,7 +182,7 @@ struct BwdSmem {
 	uint64_t empty[BWD_STAGES];            // mbarrier: all 8 warps are done reading the stage
 	float w[8][16 * STASH_LD];
 	float u[8][16 * STASH_LD];
-	float4 rowinfo[8][16 * 2];            // per stashed row: (conic.xyz, id bits), (mean2D.xy, opacity, -): rows outlive their staging buffer
+	uint32_t rowid[8][16];                 // Gaussian id of each stashed row (rows outlive their staging buffer; the flush re-reads the record)
 	float dlp[8][3 * 32];                  // dL/dpixel of the warp's 32 pixels, channel-major: B operand of the colour product
 	float wgt[8 * 32];                     // (1, qx, qy, qx^2, qx*qy, qy^2, 0, 0) of the 32 warp-local pixels: B operand of the moment product
 };
@@ -244,6 +250,11 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 		if (nrows == 0) return;
 		for (uint32_t r = nrows; r < 16; r++) { sw[r * STASH_LD + lane] = 0.f; su[r * STASH_LD + lane] = 0.f; }
 		__syncwarp();
+		if (ft == 0)                                                                 // the epilogue re-reads the rows' records: pull them into L1 behind the MMAs
+		{
+			if (fg < nrows) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 3 * (size_t)S.rowid[warp][fg]));
+			if (fg + 8 < nrows) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 3 * (size_t)S.rowid[warp][fg + 8]));
+		}
 		float dw[4] = { 0.f, 0.f, 0.f, 0.f }, du[4] = { 0.f, 0.f, 0.f, 0.f };
 		const float* dl = S.dlp[warp] + (fg < 3 ? fg : 0) * 32;
 #pragma unroll
@@ -278,8 +289,8 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 			const uint32_t row = fg + 8 * h;
 			if (ft == 0 && row < nrows)
 			{
-				const float4 r0 = S.rowinfo[warp][2 * row], r1 = S.rowinfo[warp][2 * row + 1];
-				const uint32_t gid = __float_as_uint(r0.w);
+				const uint32_t gid = S.rowid[warp][row];
+				const float4 r0 = __ldg(rec + 3 * (size_t)gid), r1 = __ldg(rec + 3 * (size_t)gid + 1);      // L2-resident: staged moments ago
 				const float X = r1.x - cxw, Y = r1.y - cyw, o = r1.z;
 				const float M0 = dw[2 * h], Mx = dw[2 * h + 1];
 				const float Sx = X * M0 - Mx, Sy = Y * M0 - My;
@@ -383,8 +394,7 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 				}
 				sw[nrows * STASH_LD + lane] = wv;
 				su[nrows * STASH_LD + lane] = uv;
-				if (lane == 0) S.rowinfo[warp][2 * nrows] = make_float4(r0.x, r0.y, r0.z, __uint_as_float(S.id[buf][jj]));
-				if (lane == 1) S.rowinfo[warp][2 * nrows + 1] = r1;
+				if (lane == 0) S.rowid[warp][nrows] = S.id[buf][jj];
 				nrows++;
 				if (nrows == 16) flush_rows();
 			}

@@ -9,11 +9,25 @@ receives the forward intermediates in the reference's GeometryState layouts).
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import torch
 
 from gs_b200 import lib as _lib
 from gs_b200.lib import GsbCamera, GsbDebug, GsbGrads, GsbQuant, GsbScene, BlobAllocator, f32, ptr
+
+
+def _carve_f32(device, shapes):
+    """The gradient outputs as views of ONE allocation (each starting on a 256-byte boundary).  Eight separate mid-size
+    tensors per backward (1-100 MB, different sizes) fragment the caching allocator's split blocks and provoke a cudaMalloc
+    inside the training loop every now and then (measured: 1-90 ms); one request of a constant size is always reused."""
+    sizes = [int(math.prod(sh)) for sh in shapes]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 63) // 64 * 64
+    flat = torch.empty(max(total, 1), dtype=torch.float32, device=device)
+    return [flat[o:o + n].view(sh) for o, n, sh in zip(offs, sizes, shapes)]
 
 
 def _device_of(means3D: torch.Tensor) -> torch.device:
@@ -91,7 +105,7 @@ def _forward(background, means3D, colors, opacity, scales, rotations, scale_modi
         cam = _camera(device, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, prefiltered, keep)
         out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
         radii = torch.empty((P,), dtype=torch.int32, device=device)
-        geom, binning, img = BlobAllocator(device), BlobAllocator(device), BlobAllocator(device)
+        geom, binning, img = BlobAllocator(device, "geom"), BlobAllocator(device, "binning"), BlobAllocator(device, "image")
         dbg_ptr = None
         if debug_out is not None:
             d = dict(depths=torch.zeros(P, device=device), means2D=torch.zeros(P, 2, device=device),
@@ -152,8 +166,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         if accumulate_into is not None:
             outs = list(accumulate_into)
         else:
-            e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
-            outs = [e(P, 3), e(P, 3), e(P, 1), e(P, 3), e(P, 6), e(P, M, 3), e(P, 3), e(P, 4)]
+            outs = _carve_f32(device, [(P, 3), (P, 3), (P, 1), (P, 3), (P, 6), (P, M, 3), (P, 3), (P, 4)])
         conic = torch.empty((P, 4), dtype=torch.float32, device=device) if want_conic else None
         g = GsbGrads(ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), ptr(outs[4]), ptr(outs[5]), ptr(outs[6]), ptr(outs[7]),
                      ptr(conic), 1 if accumulate_into is not None else 0)

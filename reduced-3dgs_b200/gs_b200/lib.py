@@ -159,16 +159,30 @@ class BlobAllocator:
     The ctypes callback closes over a plain list, NOT over `self`: a bound-method callback would form a reference
     cycle (self -> cb -> self) and keep the blobs alive until the cyclic GC runs, defeating the caching allocator."""
 
-    def __init__(self, device):
+    # High-water mark of the sizes requested per (device, blob kind).  The instance count R — and with it the binning blob —
+    # changes from view to view; requests of slightly different sizes make the caching allocator split / mismatch its cached
+    # blocks and fall back to cudaMalloc (1-40 ms, inside a training step) every now and then.  Asking for the largest size
+    # seen so far makes every request after the first pass over the views identical, so a freed block always fits.
+    _hwm = {}
+
+    def __init__(self, device, kind: str = ""):
         holder = []
+        key = (str(device), kind)
+        hwm = BlobAllocator._hwm
 
         def alloc(_user, nbytes, _holder=holder, _device=device):
-            # round up to 1/16 of the next power of two: the instance count R changes a little from view to view, and the
-            # caching allocator can only reuse a block that is at least as large as the request
+            # round up to 1/16 of the next power of two, then to the high-water mark (unless that is over twice the request:
+            # a much smaller workload has started, restart the mark)
             nbytes = int(nbytes)
             if nbytes > (1 << 20):
                 q = 1 << (nbytes.bit_length() - 5)
                 nbytes = (nbytes + q - 1) // q * q
+                if kind:
+                    top = hwm.get(key, 0)
+                    if nbytes <= top <= 2 * nbytes:
+                        nbytes = top
+                    else:
+                        hwm[key] = nbytes
             t = torch.empty(nbytes, dtype=torch.uint8, device=_device)
             _holder.append(t)
             return t.data_ptr()
