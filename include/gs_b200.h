@@ -137,6 +137,18 @@ GSB_API int gsb_forward(const GsbScene* scene, const GsbCamera* cam,
                 float* out_color, int32_t* radii, int64_t* num_rendered,
                 const GsbDebug* debug, void* stream);
 
+/* Forward that also gathers the per-Gaussian visibility statistics of the SH-culling pass
+ * (forward.cu:560-564 `calculate_mean_transmittance`, driven by reduced_3dgs.cu:96-152):
+ *   touched_pixels[i]    = number of pixels Gaussian i contributed to              (int32 [P], zeroed here)
+ *   transmittance_sum[i] = sum over those pixels of the transmittance T in front   (float [P], zeroed here)
+ * Everything else as gsb_forward. */
+GSB_API int gsb_forward_statistics(const GsbScene* scene, const GsbCamera* cam,
+                gsb_alloc_fn geom_alloc, void* geom_user,
+                gsb_alloc_fn binning_alloc, void* binning_user,
+                gsb_alloc_fn image_alloc, void* image_user,
+                float* out_color, int32_t* radii, int64_t* num_rendered,
+                int32_t* touched_pixels, float* transmittance_sum, void* stream);
+
 /* Backward from the blobs of the paired forward.  Fully asynchronous on `stream`. */
 GSB_API int gsb_backward(const GsbScene* scene, const GsbCamera* cam, int64_t num_rendered, const int32_t* radii,
                  const char* geom_blob, const char* binning_blob, const char* image_blob,
@@ -156,6 +168,36 @@ GSB_API int gsb_export_image(const char* image_blob, int32_t width, int32_t heig
 
 /* Test helper: the fused de-quantisation on its own -> activated scales [P,3], normalised rotations [P,4]. */
 GSB_API int gsb_debug_dequant(const GsbQuant* quant, int32_t P, float* scales, float* rotations, void* stream);
+
+/* ---- reduced-3dgs tools on either side of the rasterizer (reference reduced_3dgs.h:19-67, bound in ext.cpp:21-25) ----
+ *
+ * One camera's update of the SH-culling colour statistics (the body of the camera loop of
+ * Reduced3DGS::calculateColourVariance, reduced_3dgs.cu:150-201, with calculateColourCUDA of reduced_3dgs/sh_culling.cu fused in):
+ * t = transmittance_sum / max(touched_pixels, 1); weight_sum += t; weight_sq_sum += t^2;
+ * distance_accum[P,3] += t * ||colour(deg 3) - colour(deg d)||; mean[P,3] / variance[P,3] updated for visible Gaussians (radii > 0).
+ * shs is the dense [P,M,3] tensor with M >= 16 (the reference hard-codes a 4-slot colour table, i.e. max_sh_degree = 3). */
+GSB_API int gsb_sh_statistics_update(int32_t P, int32_t M, const int32_t* degrees, const float* means3D, const float* campos /* [3] */,
+                const float* shs, const int32_t* radii, const int32_t* touched_pixels, const float* transmittance_sum,
+                float* weight_sum /* [P] */, float* weight_sq_sum /* [P] */, float* distance_accum /* [P,3] */,
+                float* mean /* [P,3] */, float* variance /* [P,3] */, void* stream);
+
+/* pixel_sizes[i] = min over cameras of the world-space length of one pixel at Gaussian centre i, 10000 if no camera sees it
+ * (Reduced3DGS::calculatePixelSize, reduced_3dgs.cu:246-268 + transformCentersNDCCUDA, redundancy_score.cu:45-101).
+ * w2ndc / w2ndc_inverse: [n_cameras,4,4] exactly as the reference passes them; heights / widths: int32 [n_cameras] on the device. */
+GSB_API int gsb_min_projected_pixel_size(int32_t P, const float* means3D, int32_t n_cameras, const float* w2ndc, const float* w2ndc_inverse,
+                const int32_t* image_heights, const int32_t* image_widths, float* pixel_sizes /* [P] */, void* stream);
+
+/* redundancy_values[i] = number of the knn neighbours whose (scale + sphere_radius[i]) ellipsoid contains centre i,
+ * intersection_mask[i,k] = that test per neighbour (Reduced3DGS::intersectionTest, reduced_3dgs.cu:205-243 +
+ * sphereEllipsoidIntersectionCUDA / buildRotationMatrixCUDA, redundancy_score.cu:119-205). */
+GSB_API int gsb_sphere_ellipsoid_intersection(int32_t P, const float* means3D, const float* scales, const float* rotations,
+                const int32_t* neighbours /* [P,knn] */, const float* sphere_radius /* [P] */, int32_t knn,
+                int32_t* redundancy_values /* [P] */, uint8_t* intersection_mask /* [P,knn] */, void* stream);
+
+/* minimum_redundancy_values[n] = min(P, min over (i,k) with intersection_mask[i,k] and neighbours[i,k] == n of redundancy_values[i])
+ * (Reduced3DGS::assignFinalRedundancyValue, reduced_3dgs.cu:270-287 + findMinimumRedundancyValueCUDA, redundancy_score.cu:6-27). */
+GSB_API int gsb_min_redundancy_value(int32_t P, const int32_t* redundancy_values, const int32_t* neighbours, const uint8_t* intersection_mask,
+                int32_t knn, int32_t* minimum_redundancy_values /* [P] */, void* stream);
 
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 GSB_API uint64_t gsb_launch_count(void);

@@ -1,14 +1,17 @@
 """Build the UNMODIFIED reference rasterizer into oracle/_ref/ (test infrastructure only).
 
 The reference (graphdeco-inria/reduced-3dgs, submodules/diff-gaussian-rasterization) is CUDA and
-needs GLM, whose submodule directory is empty in /root/reference.  We compile the four hot-path
-translation units where they lie (no sources are copied), against the minimal GLM stand-in in
+needs GLM, whose submodule directory is empty in /root/reference.  We compile its translation units
+(rasterizer + the reduced_3dgs tools) where they lie (no sources are copied), against the minimal GLM stand-in in
 oracle/glm_shim/, with the flags torch's BuildExtension would pass for the reference's setup.py
 (setup.py:23-27: only the GLM include path and --disable-warnings; arch = the GPU's: sm_100).
 
 Outputs (git-ignored, but shipped to the GPU box by gpurun):
-    oracle/_ref/_refC.so      pybind module: rasterize_gaussians, rasterize_gaussians_backward,
-                              rasterize_gaussians_variableSH_bands, mark_visible
+    oracle/_ref/_refC.so      pybind module with the reference's nine entry points (ext.cpp:17-25):
+                              rasterize_gaussians, rasterize_gaussians_backward,
+                              rasterize_gaussians_variableSH_bands, mark_visible, calculate_colours_variance,
+                              sphere_ellipsoid_intersection, allocate_minimum_redundancy_value,
+                              find_minimum_projected_pixel_size, kmeans_cuda
 
 Uses: GPU-vs-GPU parity tests (tests/test_gpu_vs_reference.py), golden fixture generation
 (tests/golden/make_golden.py) and the `bench.py --impl reference` arm.  Never used by the product.
@@ -37,7 +40,9 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
     if not reference_available():
         return SO if os.path.isfile(SO) else None
     srcs = [os.path.join(DGR, "cuda_rasterizer", f) for f in ("rasterizer_impl.cu", "forward.cu", "backward.cu")]
-    srcs += [os.path.join(DGR, "rasterize_points.cu"), os.path.join(HERE, "ref_binding.cpp")]
+    srcs += [os.path.join(DGR, "rasterize_points.cu"), os.path.join(DGR, "reduced_3dgs.cu")]
+    srcs += [os.path.join(DGR, "reduced_3dgs", f) for f in ("kmeans.cu", "redundancy_score.cu", "sh_culling.cu")]
+    srcs += [os.path.join(HERE, "ref_binding.cpp")]
     deps = srcs + [os.path.join(HERE, "glm_shim", "glm", "glm.hpp"), __file__]
     if not force and os.path.isfile(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO

@@ -8,12 +8,15 @@
 // parity checks and for the `bench.py --impl reference` arm.  Nothing in the
 // product (reduced-3dgs_b200/) includes it.
 //
-// Only the symbols the reference hot path uses are provided (forward.cu,
-// backward.cu, rasterizer_impl.cu): vec3, vec4, mat3 (column-major, m[c][r]),
-// dot, length, max, sign, transpose and the arithmetic operators.  The
+// Only the symbols the reference uses are provided (forward.cu, backward.cu,
+// rasterizer_impl.cu, reduced_3dgs.cu, reduced_3dgs/*.cu): vec1, vec3, vec4, bvec3,
+// mat3 / mat4 (column-major, m[c][r]), dot, length, max, sign, pow, all,
+// lessThanEqual, greaterThanEqual, transpose and the arithmetic operators.  The
 // summation orders follow upstream GLM's generic (non-SIMD) code paths:
 //   dot(a,b)      = (a.x*b.x + a.y*b.y) + a.z*b.z
 //   (A*B)[c][r]   = (A[0][r]*B[c][0] + A[1][r]*B[c][1]) + A[2][r]*B[c][2]
+//   M4*v          = (M[0]*v.x + M[1]*v.y) + (M[2]*v.z + M[3]*v.w)
+//   v*M3          = (dot(M[0],v), dot(M[1],v), dot(M[2],v))   (row vector times matrix)
 //   length(v)     = sqrt(dot(v,v))
 //   sign(x)       = (0 < x) - (x < 0)
 #pragma once
@@ -27,10 +30,19 @@
 
 namespace glm {
 
+struct vec1 {
+	float x;
+	GLM_SHIM_FN vec1() : x(0) {}
+	GLM_SHIM_FN explicit vec1(float s) : x(s) {}
+};
+struct vec4;
+
 struct vec3 {
 	float x, y, z;
 	GLM_SHIM_FN vec3() : x(0), y(0), z(0) {}
 	GLM_SHIM_FN explicit vec3(float s) : x(s), y(s), z(s) {}
+	GLM_SHIM_FN explicit vec3(int s) : x(float(s)), y(float(s)), z(float(s)) {}
+	GLM_SHIM_FN explicit vec3(const vec4& v);                    // drops w
 	template <typename A, typename B, typename C>
 	GLM_SHIM_FN vec3(A a, B b, C c) : x(float(a)), y(float(b)), z(float(c)) {}
 	GLM_SHIM_FN float& operator[](int i) { return (&x)[i]; }
@@ -48,9 +60,16 @@ struct vec4 {
 	GLM_SHIM_FN explicit vec4(float s) : x(s), y(s), z(s), w(s) {}
 	template <typename A, typename B, typename C, typename D>
 	GLM_SHIM_FN vec4(A a, B b, C c, D d) : x(float(a)), y(float(b)), z(float(c)), w(float(d)) {}
+	GLM_SHIM_FN vec4(const vec3& v, const vec1& s) : x(v.x), y(v.y), z(v.z), w(s.x) {}
+	GLM_SHIM_FN vec4(const vec3& v, float s) : x(v.x), y(v.y), z(v.z), w(s) {}
 	GLM_SHIM_FN float& operator[](int i) { return (&x)[i]; }
 	GLM_SHIM_FN const float& operator[](int i) const { return (&x)[i]; }
 };
+
+GLM_SHIM_FN vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
+GLM_SHIM_FN vec4 operator+(const vec4& a, const vec4& b) { return vec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+GLM_SHIM_FN vec4 operator*(const vec4& a, const vec4& b) { return vec4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+GLM_SHIM_FN vec4 operator*(const vec4& a, float s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
 GLM_SHIM_FN vec3 operator+(const vec3& a, const vec3& b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
 GLM_SHIM_FN vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -60,6 +79,16 @@ GLM_SHIM_FN vec3 operator*(const vec3& a, float s) { return vec3(a.x * s, a.y * 
 GLM_SHIM_FN vec3 operator*(float s, const vec3& a) { return vec3(s * a.x, s * a.y, s * a.z); }
 GLM_SHIM_FN vec3 operator/(const vec3& a, float s) { return vec3(a.x / s, a.y / s, a.z / s); }
 GLM_SHIM_FN vec3 operator+(const vec3& a, float s) { return vec3(a.x + s, a.y + s, a.z + s); }
+GLM_SHIM_FN vec3 operator/(const vec3& a, const vec3& b) { return vec3(a.x / b.x, a.y / b.y, a.z / b.z); }
+GLM_SHIM_FN vec3 pow(const vec3& a, const vec3& e) { return vec3(powf(a.x, e.x), powf(a.y, e.y), powf(a.z, e.z)); }
+
+struct bvec3 {
+	bool x, y, z;
+	GLM_SHIM_FN bvec3(bool a, bool b, bool c) : x(a), y(b), z(c) {}
+};
+GLM_SHIM_FN bvec3 lessThanEqual(const vec3& a, const vec3& b) { return bvec3(a.x <= b.x, a.y <= b.y, a.z <= b.z); }
+GLM_SHIM_FN bvec3 greaterThanEqual(const vec3& a, const vec3& b) { return bvec3(a.x >= b.x, a.y >= b.y, a.z >= b.z); }
+GLM_SHIM_FN bool all(const bvec3& v) { return v.x && v.y && v.z; }
 
 GLM_SHIM_FN float dot(const vec3& a, const vec3& b)
 {
@@ -116,6 +145,29 @@ GLM_SHIM_FN mat3 operator*(float s, const mat3& m)
 	return r;
 }
 GLM_SHIM_FN mat3 operator*(const mat3& m, float s) { return s * m; }
+// row vector times matrix (type_mat3x3.inl: operator*(column_type const& v, mat const& m))
+GLM_SHIM_FN vec3 operator*(const vec3& v, const mat3& m)
+{
+	return vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z,
+		m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z,
+		m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z);
+}
+
+// Column-major 4x4, only what redundancy_score.cu needs: M * v.
+struct mat4 {
+	vec4 c[4];
+	GLM_SHIM_FN vec4& operator[](int i) { return c[i]; }
+	GLM_SHIM_FN const vec4& operator[](int i) const { return c[i]; }
+};
+GLM_SHIM_FN vec4 operator*(const mat4& m, const vec4& v)
+{
+	const vec4 Mul0 = m[0] * vec4(v.x), Mul1 = m[1] * vec4(v.y);
+	const vec4 Add0 = Mul0 + Mul1;
+	const vec4 Mul2 = m[2] * vec4(v.z), Mul3 = m[3] * vec4(v.w);
+	const vec4 Add1 = Mul2 + Mul3;
+	return Add0 + Add1;
+}
+
 GLM_SHIM_FN mat3 transpose(const mat3& m)
 {
 	return mat3(m[0][0], m[1][0], m[2][0],

@@ -155,6 +155,115 @@ def render_forward(geom, binning, bg, W, H, f64=False):
     return dict(final_T=final_T, n_contrib=n_contrib, color=color, borderline=borderline.astype(bool))
 
 
+def render_forward_stats(geom, binning, bg, W, H):
+    """renderCUDA with calculate_mean_transmittance (forward.cu:560-564): render_forward() + touched_pixels int32 [P] and
+    transmittance_sum float64 [P] (the reference accumulates in fp32 with atomics in arbitrary order)."""
+    bg = _np(bg, np.float32)
+    colors = _np(geom["rgb"], np.float32)
+    P = colors.shape[0]
+    final_T = np.zeros((H, W), np.float32)
+    n_contrib = np.zeros((H, W), np.uint32)
+    color = np.zeros((3, H, W), np.float32)
+    borderline = np.zeros((H, W), np.uint8)
+    touched = np.zeros(P, np.int32)
+    tsum = np.zeros(P, np.float64)
+    lib().gso_render_forward_stats(W, H, _p(binning["ranges"], u32p), _p(binning["point_list"], u32p),
+                                   _p(geom["means2D"], f32p), _p(colors, f32p), _p(geom["conic_opacity"], f32p), _p(bg, f32p),
+                                   _p(final_T, f32p), _p(n_contrib, u32p), _p(color, f32p), _p(borderline, u8p),
+                                   _p(touched, i32p), _p(tsum, f64p))
+    return dict(final_T=final_T, n_contrib=n_contrib, color=color, borderline=borderline.astype(bool),
+                touched_pixels=touched, transmittance_sum=tsum)
+
+
+def sh_colours(means3D, campos, shs, degrees):
+    """reduced_3dgs/sh_culling.cu:6-57: colours [P,4,3]; slot k of a Gaussian is written only for k <= its degree (else 0)."""
+    means3D, shs = _np(means3D, np.float32), _np(shs, np.float32)
+    degrees = _np(degrees, np.int32).reshape(-1)
+    campos = _np(campos, np.float32).reshape(3)
+    P, M = shs.shape[0], shs.shape[1]
+    out = np.zeros((P, 4, 3), np.float32)
+    lib().gso_sh_colours(P, M, _p(degrees, i32p), _p(means3D, f32p), _p(campos, f32p), _p(shs, f32p), _p(out, f32p))
+    return out
+
+
+def colours_variance(cam_positions, means3D, opacity, scales, rotations, viewmatrices, projmatrices, tan_fovxs, tan_fovys,
+                     image_height, image_width, sh, degrees, max_sh_deg=3):
+    """Reduced3DGS::calculateColourVariance (reduced_3dgs.cu:41-203) restated with numpy fp32 in the reference's op order.
+    Returns (colour distances / wSum [P,3], variance / wSum [P,1,3], mean [P,1,3]) plus the per-camera statistics for tests."""
+    assert max_sh_deg == 3
+    means3D = _np(means3D, np.float32)
+    P = means3D.shape[0]
+    sh = _np(sh, np.float32)
+    degrees = _np(degrees, np.int32).reshape(-1)
+    f = np.float32
+    wsum, wsumsq = np.zeros((P, 1), f), np.zeros((P, 1), f)
+    dist_acc = np.zeros((P, 3), f)
+    mean, variance = np.zeros((P, 1, 3), f), np.zeros((P, 1, 3), f)
+    per_cam = []
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(len(cam_positions)):
+            H, W = int(image_height[i]), int(image_width[i])
+            campos = _np(cam_positions[i], np.float32)
+            geom = preprocess(means3D, scales, 1.0, rotations, opacity, sh, degrees, None, None, _np(viewmatrices[i], np.float32),
+                              _np(projmatrices[i], np.float32), campos, W, H, float(tan_fovxs[i]), float(tan_fovys[i]), None)
+            binning = bin_and_sort(geom, W, H)
+            img = render_forward_stats(geom, binning, np.zeros(3, np.float32), W, H)
+            present = geom["radii"] > 0
+            touched = img["touched_pixels"]
+            t = (img["transmittance_sum"] / np.maximum(touched, 1)).astype(f).reshape(P, 1)          # :154
+            wsum = wsum + t                                                                       # :155
+            wsumsq = wsumsq + t * t
+            colours = sh_colours(means3D, campos, sh, degrees)                                    # :158-164
+            colours[~present] = 0                                                                 # :165
+            for d in range(3):                                                                    # :167-181
+                diff = colours[:, 3:4] - colours[:, d:d + 1]
+                dist = np.sqrt((diff * diff).sum(axis=2, dtype=f)).astype(f)
+                dist[np.isnan(dist)] = 0
+                dist_acc[:, d:d + 1] = dist_acc[:, d:d + 1] + t * dist
+            colour = colours[:, 3:4]                                                              # :184
+            mean_old = mean.copy()                   # value before the update (the reference's `mean_old` ALIASES `mean`, :185)
+            coef = t / wsum
+            coef[np.isnan(coef)] = 0
+            mean[present] = mean_old[present] + coef[present].reshape(-1, 1, 1) * (colour[present] - mean_old[present])
+            # `auto mean_old = mean;` shares storage: after the in-place index_put_ both factors use the NEW mean (:196-200)
+            variance[present] = variance[present] + t[present].reshape(-1, 1, 1) * (colour[present] - mean[present]) * (colour[present] - mean[present])
+            per_cam.append(dict(touched_pixels=touched, transmittance_sum=img["transmittance_sum"], radii=geom["radii"],
+                                borderline=img["borderline"]))
+        return dist_acc / wsum, variance / wsum.reshape(-1, 1, 1), mean, per_cam
+
+
+def min_projected_pixel_size(w2ndc, w2ndc_inv, means3D, image_height, image_width):
+    """Reduced3DGS::calculatePixelSize (reduced_3dgs.cu:246-268) -> float32 [P,1]."""
+    means3D = _np(means3D, np.float32)
+    P = means3D.shape[0]
+    out = np.full((P, 1), 10000, np.float32)
+    for i in range(len(w2ndc)):
+        lib().gso_pixel_size_camera(P, _p(means3D, f32p), _p(_np(w2ndc[i], np.float32), f32p), _p(_np(w2ndc_inv[i], np.float32), f32p),
+                                    int(image_height[i]), int(image_width[i]), _p(out, f32p))
+    return out
+
+
+def sphere_ellipsoid_intersection(means3D, scales, rotations, neighbours, sphere_radius, knn):
+    """Reduced3DGS::intersectionTest (reduced_3dgs.cu:205-243) -> (redundancy int32 [P,1], mask bool [P,knn], borderline bool [P])."""
+    means3D, scales, rotations = _np(means3D, np.float32), _np(scales, np.float32), _np(rotations, np.float32)
+    neighbours, sphere_radius = _np(neighbours, np.int32), _np(sphere_radius, np.float32).reshape(-1)
+    P = means3D.shape[0]
+    red, mask, bl = np.zeros((P, 1), np.int32), np.zeros((P, knn), np.uint8), np.zeros(P, np.uint8)
+    lib().gso_sphere_ellipsoid(P, _p(means3D, f32p), _p(scales, f32p), _p(rotations, f32p), _p(neighbours, i32p), _p(sphere_radius, f32p),
+                               int(knn), _p(red, i32p), _p(mask, u8p), _p(bl, u8p))
+    return red, mask.astype(bool), bl.astype(bool)
+
+
+def min_redundancy_value(redundancy_values, neighbours, intersection_mask, knn):
+    """Reduced3DGS::assignFinalRedundancyValue (reduced_3dgs.cu:270-287) -> int32 [P,1]."""
+    red = _np(redundancy_values, np.int32).reshape(-1)
+    nb, mask = _np(neighbours, np.int32), _np(intersection_mask).astype(np.uint8)
+    P = red.shape[0]
+    out = np.full((P, 1), P, np.int32)
+    lib().gso_min_redundancy(P, _p(red, i32p), _p(nb, i32p), _p(mask, u8p), int(knn), _p(out, i32p))
+    return out
+
+
 def forward(means3D, opacities, scales=None, rotations=None, shs=None, degrees=None, colors_precomp=None,
             cov3D_precomp=None, *, viewmatrix, projmatrix, campos, bg, W, H, tan_fovx, tan_fovy, scale_modifier=1.0,
             packed=None, prune_mask=None):

@@ -48,7 +48,7 @@ void prof_end(int kid, cudaStream_t stream)
 	g_prof_cur = nullptr;
 }
 static const char* kKernelNames[K_COUNT] = { "preprocess", "tile_scan", "scatter", "tile_sort_large", "unused4", "tile_sort", "unused6",
-	"render_forward", "render_backward", "preprocess_backward", "mark_visible" };
+	"render_forward", "render_backward", "preprocess_backward", "mark_visible", "tools", "kmeans" };
 
 int launch_debug_dequant(const GsbQuant*, int, float*, float*, cudaStream_t);
 int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, const ImageState&, const BinPlan&, int32_t*, const GsbDebug*, cudaStream_t);
@@ -56,7 +56,12 @@ int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t)
 int launch_tile_scan(const ImageState&, const GeomState&, const BinPlan&, int, int, cudaStream_t);
 int launch_binning(const GeomState&, const BinningState&, const ImageState&, const BinPlan&, int, long long, int, int, cudaStream_t);
 int launch_export_binning(const GeomState&, const BinningState&, const ImageState&, int, int, uint64_t*, uint32_t*, cudaStream_t);
-int launch_render_forward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, float*, cudaStream_t);
+int launch_render_forward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, float*, int32_t*, float*, cudaStream_t);
+int launch_sh_stats_update(int, int, const int*, const float*, const float*, const float*, const int*, const int*, const float*, float*, float*,
+	float*, float*, float*, cudaStream_t);
+int launch_pixel_size(int, const float*, int, const float*, const float*, const int*, const int*, float*, cudaStream_t);
+int launch_sphere_ellipsoid(int, const float*, const float*, const float*, const int*, const float*, int, int*, uint8_t*, cudaStream_t);
+int launch_min_redundancy(int, const int*, const int*, const uint8_t*, int, int*, cudaStream_t);
 int launch_render_backward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, const float*, float*, cudaStream_t);
 int launch_preprocess_backward(const GsbScene*, const GsbCamera*, const GeomState&, const int32_t*, const float*, const GsbGrads*, float, cudaStream_t);
 
@@ -127,9 +132,10 @@ int gsb_profile_read(int max_entries, const char** names, double* total_ms, uint
 	return k;
 }
 
-int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_alloc, void* geom_user,
+static int forward_impl(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_alloc, void* geom_user,
 	gsb_alloc_fn binning_alloc, void* binning_user, gsb_alloc_fn image_alloc, void* image_user,
-	float* out_color, int32_t* radii, int64_t* num_rendered, const GsbDebug* debug, void* stream_)
+	float* out_color, int32_t* radii, int64_t* num_rendered, const GsbDebug* debug, int32_t* touched_pixels, float* transmittance,
+	void* stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	if (int e = check_scene(scene, cam)) return e;
@@ -166,8 +172,70 @@ int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_a
 	if (!bin_blob) { set_error("binning allocation failed"); return GSB_ENOMEM; }
 	BinningState b = BinningState::carve(bin_blob, R);
 	if (int e = launch_binning(g, b, img, plan, P, R, W, H, stream)) return e;
-	if (int e = launch_render_forward(img, b, g, W, H, cam->background, out_color, stream)) return e;
+	if (int e = launch_render_forward(img, b, g, W, H, cam->background, out_color, touched_pixels, transmittance, stream)) return e;
 	return GSB_OK;
+}
+
+int gsb_forward(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_alloc, void* geom_user,
+	gsb_alloc_fn binning_alloc, void* binning_user, gsb_alloc_fn image_alloc, void* image_user,
+	float* out_color, int32_t* radii, int64_t* num_rendered, const GsbDebug* debug, void* stream)
+{
+	return forward_impl(scene, cam, geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user, out_color, radii,
+		num_rendered, debug, nullptr, nullptr, stream);
+}
+
+int gsb_forward_statistics(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_alloc, void* geom_user,
+	gsb_alloc_fn binning_alloc, void* binning_user, gsb_alloc_fn image_alloc, void* image_user,
+	float* out_color, int32_t* radii, int64_t* num_rendered, int32_t* touched_pixels, float* transmittance_sum, void* stream)
+{
+	if (!scene || scene->P < 0) { set_error("scene is NULL"); return GSB_EINVAL; }
+	if (scene->P > 0 && (!touched_pixels || !transmittance_sum)) { set_error("statistics output pointers missing"); return GSB_EINVAL; }
+	if (scene->P > 0)
+	{
+		// reduced_3dgs.cu:117-118: both statistics start from zero for every camera
+		GSB_CUDA_OK(cudaMemsetAsync(touched_pixels, 0, size_t(scene->P) * sizeof(int32_t), (cudaStream_t)stream));
+		GSB_CUDA_OK(cudaMemsetAsync(transmittance_sum, 0, size_t(scene->P) * sizeof(float), (cudaStream_t)stream));
+	}
+	return forward_impl(scene, cam, geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user, out_color, radii,
+		num_rendered, nullptr, touched_pixels, transmittance_sum, stream);
+}
+
+int gsb_sh_statistics_update(int32_t P, int32_t M, const int32_t* degrees, const float* means3D, const float* campos, const float* shs,
+	const int32_t* radii, const int32_t* touched_pixels, const float* transmittance_sum, float* weight_sum, float* weight_sq_sum,
+	float* distance_accum, float* mean, float* variance, void* stream)
+{
+	if (P < 0 || M < 16) { set_error("sh_statistics_update: needs P >= 0 and the full 16-coefficient SH layout (max_sh_degree 3)"); return GSB_EINVAL; }
+	if (P > 0 && (!degrees || !means3D || !campos || !shs || !radii || !touched_pixels || !transmittance_sum || !weight_sum || !weight_sq_sum ||
+		!distance_accum || !mean || !variance)) { set_error("sh_statistics_update: NULL argument"); return GSB_EINVAL; }
+	return launch_sh_stats_update(P, M, degrees, means3D, campos, shs, radii, touched_pixels, transmittance_sum, weight_sum, weight_sq_sum,
+		distance_accum, mean, variance, (cudaStream_t)stream);
+}
+
+int gsb_min_projected_pixel_size(int32_t P, const float* means3D, int32_t n_cameras, const float* w2ndc, const float* w2ndc_inverse,
+	const int32_t* image_heights, const int32_t* image_widths, float* pixel_sizes, void* stream)
+{
+	if (P < 0 || n_cameras < 0) { set_error("min_projected_pixel_size: negative size"); return GSB_EINVAL; }
+	if (P > 0 && (!means3D || !pixel_sizes || (n_cameras > 0 && (!w2ndc || !w2ndc_inverse || !image_heights || !image_widths))))
+	{ set_error("min_projected_pixel_size: NULL argument"); return GSB_EINVAL; }
+	return launch_pixel_size(P, means3D, n_cameras, w2ndc, w2ndc_inverse, image_heights, image_widths, pixel_sizes, (cudaStream_t)stream);
+}
+
+int gsb_sphere_ellipsoid_intersection(int32_t P, const float* means3D, const float* scales, const float* rotations, const int32_t* neighbours,
+	const float* sphere_radius, int32_t knn, int32_t* redundancy_values, uint8_t* intersection_mask, void* stream)
+{
+	if (P < 0 || knn < 0) { set_error("sphere_ellipsoid_intersection: negative size"); return GSB_EINVAL; }
+	if (P > 0 && (!means3D || !scales || !rotations || !sphere_radius || !redundancy_values || (knn > 0 && (!neighbours || !intersection_mask))))
+	{ set_error("sphere_ellipsoid_intersection: NULL argument"); return GSB_EINVAL; }
+	return launch_sphere_ellipsoid(P, means3D, scales, rotations, neighbours, sphere_radius, knn, redundancy_values, intersection_mask, (cudaStream_t)stream);
+}
+
+int gsb_min_redundancy_value(int32_t P, const int32_t* redundancy_values, const int32_t* neighbours, const uint8_t* intersection_mask,
+	int32_t knn, int32_t* minimum_redundancy_values, void* stream)
+{
+	if (P < 0 || knn < 0) { set_error("min_redundancy_value: negative size"); return GSB_EINVAL; }
+	if (P > 0 && (!redundancy_values || !minimum_redundancy_values || (knn > 0 && (!neighbours || !intersection_mask))))
+	{ set_error("min_redundancy_value: NULL argument"); return GSB_EINVAL; }
+	return launch_min_redundancy(P, redundancy_values, neighbours, intersection_mask, knn, minimum_redundancy_values, (cudaStream_t)stream);
 }
 
 int gsb_backward(const GsbScene* scene, const GsbCamera* cam, int64_t R, const int32_t* radii,

@@ -39,12 +39,18 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
 }
 
 // ------------------------------------------------------------------------------------------------
+// STATS = true additionally accumulates, per Gaussian, the number of pixels it contributed to and the sum of the
+// transmittance T in front of it at those pixels (forward.cu:560-564, `calculate_mean_transmittance`): one pair of
+// atomics per (warp, Gaussian) after a ballot / shuffle reduction instead of two per (pixel, Gaussian).
+template <bool STATS>
 __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __restrict__ ranges,
 	const uint32_t* __restrict__ point_list,
 	int W, int H, const float4* __restrict__ rec, const float* __restrict__ bg,
-	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, uint32_t* __restrict__ tile_max)
+	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, uint32_t* __restrict__ tile_max,
+	int32_t* __restrict__ touched_pixels, float* __restrict__ transmittance)
 {
 	__shared__ __align__(16) float4 s_rec[256 * 3];
+	__shared__ uint32_t s_id[STATS ? 256 : 1];
 	__shared__ uint32_t s_max;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -70,6 +76,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 			const uint32_t id = point_list[b + tid];
 			const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
 			s_rec[3 * tid] = r0; s_rec[3 * tid + 1] = r1; s_rec[3 * tid + 2] = r2;
+			if (STATS) s_id[tid] = id;
 		}
 		__syncthreads();
 		bool warp_done = __all_sync(0xffffffffu, done);
@@ -104,6 +111,22 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 				const bool stop = v && (test_T < 0.0001f);
 				done = done || stop;
 				v = v && !stop;
+				if (STATS)
+				{
+					const unsigned cm = __ballot_sync(0xffffffffu, v);
+					if (cm)
+					{
+						float ts = v ? T : 0.0f;
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(0xffffffffu, ts, o);
+						if (lane == 0)
+						{
+							const uint32_t gid = s_id[c0 + bit];
+							atomicAdd(&touched_pixels[gid], (int)__popc(cm));
+							atomicAdd(&transmittance[gid], ts);
+						}
+					}
+				}
 				C0 = v ? __fmaf_rn(T, __fmul_rn(r1.w, alpha), C0) : C0;
 				C1 = v ? __fmaf_rn(T, __fmul_rn(gb.x, alpha), C1) : C1;
 				C2 = v ? __fmaf_rn(T, __fmul_rn(gb.y, alpha), C2) : C2;
@@ -407,12 +430,16 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 
 // ------------------------------------------------------------------------------------------------
 int launch_render_forward(const ImageState& img, const BinningState& b, const GeomState& g, int W, int H, const float* bg,
-	float* out_color, cudaStream_t stream)
+	float* out_color, int32_t* touched_pixels, float* transmittance, cudaStream_t stream)
 {
 	const dim3 grid((W + GSB_TILE_X - 1) / GSB_TILE_X, (H + GSB_TILE_Y - 1) / GSB_TILE_Y);
 	ProfScope prof(K_RENDER_FWD, stream);
-	render_forward_kernel<<<grid, 256, 0, stream>>>(img.ranges, b.point_list, W, H, g.rec, bg,
-		img.final_T, img.n_contrib, out_color, img.tile_max_contrib);
+	if (touched_pixels && transmittance)
+		render_forward_kernel<true><<<grid, 256, 0, stream>>>(img.ranges, b.point_list, W, H, g.rec, bg,
+			img.final_T, img.n_contrib, out_color, img.tile_max_contrib, touched_pixels, transmittance);
+	else
+		render_forward_kernel<false><<<grid, 256, 0, stream>>>(img.ranges, b.point_list, W, H, g.rec, bg,
+			img.final_T, img.n_contrib, out_color, img.tile_max_contrib, nullptr, nullptr);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
 	return GSB_OK;

@@ -92,7 +92,7 @@ def _scene(device, means3D, colors, opacity, scales, rotations, scale_modifier, 
 
 def _forward(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix,
              tan_fovx, tan_fovy, image_height, image_width, sh, degrees, campos, prefiltered, debug, packed_counts=None,
-             prune_mask=None, quant=None, debug_out=None):
+             prune_mask=None, quant=None, debug_out=None, statistics=None):
     if means3D.ndimension() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")          # rasterize_points.cu:158-161
     device = _device_of(means3D)
@@ -116,8 +116,13 @@ def _forward(background, means3D, colors, opacity, scales, rotations, scale_modi
             dbg = GsbDebug(*[ptr(d[k]) for k in ("depths", "means2D", "cov3D", "conic_opacity", "rgb", "tiles_touched", "clamped")])
             dbg_ptr = C.pointer(dbg)
         R = C.c_int64(0)
-        st = L.gsb_forward(C.byref(scene), C.byref(cam), geom.cb, None, binning.cb, None, img.cb, None,
-                           out_color.data_ptr(), ptr(radii), C.byref(R), dbg_ptr, _lib.current_stream(device))
+        if statistics is not None:                               # (touched_pixels int32 [P,1], transmittance_sum f32 [P,1]) to fill
+            st = L.gsb_forward_statistics(C.byref(scene), C.byref(cam), geom.cb, None, binning.cb, None, img.cb, None,
+                                          out_color.data_ptr(), ptr(radii), C.byref(R), ptr(statistics[0]), ptr(statistics[1]),
+                                          _lib.current_stream(device))
+        else:
+            st = L.gsb_forward(C.byref(scene), C.byref(cam), geom.cb, None, binning.cb, None, img.cb, None,
+                               out_color.data_ptr(), ptr(radii), C.byref(R), dbg_ptr, _lib.current_stream(device))
         _lib.check(st)
         if debug:
             torch.cuda.synchronize(device)                      # reference CHECK_CUDA(debug) semantics, auxiliary.h:161-168
@@ -179,6 +184,94 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     if want_conic:
         return tuple(outs) + (conic,)
     return tuple(outs)
+
+
+def calculate_colours_variance(cam_positions, means3D, opacity, scales, rotations, cam_viewmatrices, cam_projmatrices, tan_fovxs,
+                               tan_fovys, image_height, image_width, sh, degrees, max_sh_deg):
+    """reduced_3dgs.h:28-43 Reduced3DGS::calculateColourVariance (reduced_3dgs.cu:41-203) ->
+    (average colour distance to each lower SH truncation [P, max_sh_deg], weighted colour variance [P,1,3], weighted mean colour [P,1,3]).
+    Per camera: one forward with the visibility statistics on (gsb_forward_statistics) + one fused statistics kernel
+    (gsb_sh_statistics_update) in place of the reference's ~30 ATen ops; the camera parameters are read back once, not per camera."""
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")          # reduced_3dgs.cu:57-60
+    device = _device_of(means3D)
+    if int(max_sh_deg) != 3:
+        raise RuntimeError("calculate_colours_variance: the reference's colour table has 4 slots per Gaussian "
+                           "(reduced_3dgs/sh_culling.cu:21), i.e. it is only meaningful for max_sh_deg == 3")
+    L = _lib.lib()
+    P = int(means3D.size(0))
+    n_cams = int(cam_positions.size(0))
+    M = int(sh.size(1)) if (P != 0 and sh.size(0) != 0) else 0
+    f = lambda t: f32(t, device)
+    zeros = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)
+    wsum, wsumsq, dist, mean, var = zeros(P, 1), zeros(P, 1), zeros(P, 3), zeros(P, 1, 3), zeros(P, 1, 3)
+    if P == 0 or n_cams == 0:
+        return dist / wsum, var / wsum.view(-1, 1, 1), mean
+    means3D, sh, cam_positions = f(means3D), f(sh), f(cam_positions)
+    views, projs = f(cam_viewmatrices), f(cam_projmatrices)
+    deg = degrees.to(device=device, dtype=torch.int32).contiguous()
+    Hs, Ws = [int(v) for v in image_height.cpu().tolist()], [int(v) for v in image_width.cpu().tolist()]
+    txs, tys = [float(v) for v in tan_fovxs.cpu().tolist()], [float(v) for v in tan_fovys.cpu().tolist()]
+    bg = zeros(3)                                             # reduced_3dgs.cu:112 background is irrelevant here
+    empty = torch.empty(0)
+    touched = torch.empty((P, 1), dtype=torch.int32, device=device)
+    tsum = torch.empty((P, 1), dtype=torch.float32, device=device)
+    stream = _lib.current_stream(device)
+    for i in range(n_cams):
+        _, _, radii, _, _, _ = _forward(bg, means3D, empty, opacity, scales, rotations, 1.0, empty, views[i], projs[i], txs[i], tys[i],
+                                        Hs[i], Ws[i], sh, deg, cam_positions[i], False, False, statistics=(touched, tsum))
+        with torch.cuda.device(device):
+            _lib.check(L.gsb_sh_statistics_update(P, M, ptr(deg), ptr(means3D), cam_positions[i].data_ptr(), ptr(sh), ptr(radii), ptr(touched),
+                                                  ptr(tsum), ptr(wsum), ptr(wsumsq), ptr(dist), ptr(mean), ptr(var), stream))
+    return dist / wsum, var / wsum.view(-1, 1, 1), mean
+
+
+def find_minimum_projected_pixel_size(w2ndc_transforms, w2ndc_transforms_inverse, means3D, image_height, image_width):
+    """reduced_3dgs.h:61-66 Reduced3DGS::calculatePixelSize (reduced_3dgs.cu:246-268) -> float [P,1]."""
+    device = _device_of(means3D)
+    L = _lib.lib()
+    P, n = int(means3D.size(0)), int(w2ndc_transforms.size(0))
+    out = torch.empty((P, 1), dtype=torch.float32, device=device)
+    if P == 0:
+        return out
+    i32 = lambda t: t.to(device=device, dtype=torch.int32).contiguous()
+    m, mi, xyz, hs, ws = f32(w2ndc_transforms, device), f32(w2ndc_transforms_inverse, device), f32(means3D, device), i32(image_height), i32(image_width)
+    with torch.cuda.device(device):
+        _lib.check(L.gsb_min_projected_pixel_size(P, ptr(xyz), n, ptr(m), ptr(mi), ptr(hs), ptr(ws), ptr(out), _lib.current_stream(device)))
+    return out
+
+
+def sphere_ellipsoid_intersection(means3D, scales, rotations, neighbours_indices, sphere_radius, knn):
+    """reduced_3dgs.h:45-51 Reduced3DGS::intersectionTest (reduced_3dgs.cu:205-243) -> (redundancy_values int32 [P,1], intersection_mask bool [P,knn])."""
+    device = _device_of(means3D)
+    L = _lib.lib()
+    P, knn = int(means3D.size(0)), int(knn)
+    red = torch.empty((P, 1), dtype=torch.int32, device=device)
+    mask = torch.empty((P, knn), dtype=torch.bool, device=device)
+    if P == 0:
+        return red, mask
+    nb = neighbours_indices.to(device=device, dtype=torch.int32).contiguous()
+    xyz, sc, rot, rad = f32(means3D, device), f32(scales, device), f32(rotations, device), f32(sphere_radius, device)
+    with torch.cuda.device(device):
+        _lib.check(L.gsb_sphere_ellipsoid_intersection(P, ptr(xyz), ptr(sc), ptr(rot), ptr(nb), ptr(rad), knn, ptr(red), ptr(mask),
+                                                       _lib.current_stream(device)))
+    return red, mask
+
+
+def allocate_minimum_redundancy_value(redundancy_values, neighbours_indices, intersection_mask, knn):
+    """reduced_3dgs.h:53-59 Reduced3DGS::assignFinalRedundancyValue (reduced_3dgs.cu:270-287) -> 1-tuple (int32 [P,1],)."""
+    device = _device_of(redundancy_values)
+    L = _lib.lib()
+    P, knn = int(redundancy_values.size(0)), int(knn)
+    out = torch.empty((P, 1), dtype=torch.int32, device=device)
+    if P == 0:
+        return (out,)
+    red = redundancy_values.to(device=device, dtype=torch.int32).contiguous()
+    nb = neighbours_indices.to(device=device, dtype=torch.int32).contiguous()
+    mask = intersection_mask.to(device=device, dtype=torch.bool).contiguous()
+    with torch.cuda.device(device):
+        _lib.check(L.gsb_min_redundancy_value(P, ptr(red), ptr(nb), ptr(mask), knn, ptr(out), _lib.current_stream(device)))
+    return (out,)
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

@@ -89,6 +89,20 @@ def lib():
         L.gsb_forward.argtypes = [C.POINTER(GsbScene), C.POINTER(GsbCamera), ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p,
                                   ALLOC_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
                                   C.POINTER(GsbDebug), C.c_void_p]
+        L.gsb_forward_statistics.restype = C.c_int
+        L.gsb_forward_statistics.argtypes = [C.POINTER(GsbScene), C.POINTER(GsbCamera), ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p,
+                                             ALLOC_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsb_sh_statistics_update.restype = C.c_int
+        L.gsb_sh_statistics_update.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 13
+        L.gsb_min_projected_pixel_size.restype = C.c_int
+        L.gsb_min_projected_pixel_size.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p]
+        L.gsb_sphere_ellipsoid_intersection.restype = C.c_int
+        L.gsb_sphere_ellipsoid_intersection.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                                        C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsb_min_redundancy_value.restype = C.c_int
+        L.gsb_min_redundancy_value.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.gsb_backward.restype = C.c_int
         L.gsb_backward.argtypes = [C.POINTER(GsbScene), C.POINTER(GsbCamera), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(GsbGrads), C.c_float, C.c_void_p]
@@ -125,7 +139,9 @@ def profile_read() -> dict:
 
 EXPORTED_SYMBOLS = ["gsb_geom_bytes", "gsb_image_bytes", "gsb_binning_bytes", "gsb_forward", "gsb_backward",
                     "gsb_mark_visible", "gsb_export_binning", "gsb_export_image", "gsb_launch_count", "gsb_last_error",
-                    "gsb_version", "gsb_profile_enable", "gsb_profile_read", "gsb_debug_dequant"]
+                    "gsb_version", "gsb_profile_enable", "gsb_profile_read", "gsb_debug_dequant", "gsb_forward_statistics",
+                    "gsb_sh_statistics_update", "gsb_min_projected_pixel_size", "gsb_sphere_ellipsoid_intersection",
+                    "gsb_min_redundancy_value"]
 
 
 def check(status: int):

@@ -51,3 +51,50 @@ def build_inputs(name):
                                               cov[:, 2, 2]], dim=1).contiguous()
         extra["colors_precomp"] = torch.rand(c["P"], 3, generator=g).contiguous()
     return c, scene, cam, bg, dL, extra
+
+
+# ---- reduced-3dgs tools: SH-culling statistics, redundancy score ------------------------------
+TOOLS_CASES = {
+    "t1": dict(P=3_000, seed=21, views=[(200, 120, -8.0), (160, 160, 5.0), (96, 128, 14.0)], log_scale=math.log(0.05), knn=6,
+               radius_scale=6.0),
+}
+
+
+def build_tools_inputs(name, P=None, views=None):
+    """Scene with mixed SH degrees, a few cameras of different sizes (yaw in degrees about y), brute-force k nearest
+    neighbours (the reference takes them from simple-knn, scene/__init__.py:159-160)."""
+    import numpy as np
+    c = dict(TOOLS_CASES[name])
+    if P is not None:
+        c["P"] = P
+    if views is not None:
+        c["views"] = views
+    scene = synth.make_scene(c["P"], c["seed"], sh_degree=3, mixed_degrees=True, box=(2.4, 1.9, 1.0), log_scale_mean=c["log_scale"],
+                             M=16, near_frac=0.01)
+    cams = []
+    for (W, H, yaw) in c["views"]:
+        th = math.radians(yaw)
+        Rc2w = np.array([[math.cos(th), 0, math.sin(th)], [0, 1, 0], [-math.sin(th), 0, math.cos(th)]])
+        C = Rc2w @ np.array([0.0, 0.0, -4.0])
+        cams.append(synth.make_camera(W, H, Rc2w, -Rc2w.T @ C))
+    xyz = scene.means3D
+    knn = c["knn"]
+    nb = torch.empty((c["P"], knn), dtype=torch.int32)
+    for a in range(0, c["P"], 4096):
+        d = torch.cdist(xyz[a:a + 4096], xyz)
+        d[torch.arange(d.shape[0]), torch.arange(a, a + d.shape[0])] = float("inf")
+        nb[a:a + 4096] = d.topk(knn, dim=1, largest=False).indices.to(torch.int32)
+    return c, scene, cams, nb
+
+
+def tools_camera_tensors(cams):
+    """The stacked per-camera tensors exactly as gaussian_model.py:727-733 / scene/__init__.py:145-151 build them."""
+    return dict(
+        positions=torch.stack([c.camera_center for c in cams]),
+        views=torch.stack([c.world_view_transform for c in cams]),
+        projs=torch.stack([c.full_proj_transform for c in cams]),
+        inv_projs=torch.stack([c.full_proj_transform.inverse() for c in cams]),
+        tanx=torch.tensor([math.tan(c.FoVx * 0.5) for c in cams], dtype=torch.float32),
+        tany=torch.tensor([math.tan(c.FoVy * 0.5) for c in cams], dtype=torch.float32),
+        H=torch.tensor([c.image_height for c in cams], dtype=torch.int32),
+        W=torch.tensor([c.image_width for c in cams], dtype=torch.int32))

@@ -58,6 +58,37 @@ def run_reference(refC, name):
     return res
 
 
+def run_reference_tools(refC, name):
+    """Outputs of the reference's own reduced_3dgs entry points (ext.cpp:21-24) on a tools case."""
+    c, scene, cams, nb = cases.build_tools_inputs(name)
+    ct = {k: v.cuda() for k, v in cases.tools_camera_tensors(cams).items()}
+    sc = scene.to("cuda")
+    P, knn = c["P"], c["knn"]
+
+    def cv():
+        return refC.calculate_colours_variance(ct["positions"], sc.means3D, sc.opacity, sc.scales, sc.rotations, ct["views"], ct["projs"],
+                                               ct["tanx"], ct["tany"], ct["H"], ct["W"], sc.sh, sc.degrees, 3)
+    d, v, m = cv()
+    d2, v2, m2 = cv()
+    res = dict(cv_distance=d.cpu().numpy(), cv_variance=v.cpu().numpy(), cv_mean=m.cpu().numpy())
+    for n, a, b in (("cv_distance", d, d2), ("cv_variance", v, v2), ("cv_mean", m, m2)):
+        res["noise_" + n] = np.float32(torch.nan_to_num(a - b).abs().max().item())
+    px = refC.find_minimum_projected_pixel_size(ct["projs"], ct["inv_projs"], sc.means3D, ct["H"], ct["W"])
+    res["pixel_size"] = px.cpu().numpy()
+    half_diag = px * c["radius_scale"] * torch.sqrt(torch.tensor([3.0], device="cuda")) / 2          # scene/__init__.py:154-155
+    red, mask = refC.sphere_ellipsoid_intersection(sc.means3D, sc.scales, sc.rotations, nb.cuda(), half_diag, knn)
+    res["half_diagonal"] = half_diag.cpu().numpy()
+    res["redundancy"] = red.cpu().numpy()
+    res["intersection_mask"] = mask.cpu().numpy()
+    red1 = red + 1                                                                                    # scene/__init__.py:170-176
+    idx = torch.cat((torch.arange(P, device="cuda", dtype=torch.int).view(-1, 1), nb.cuda()), dim=1)
+    mk = torch.cat((torch.ones((P, 1), device="cuda", dtype=torch.bool), mask), dim=1)
+    res["min_redundancy"] = refC.allocate_minimum_redundancy_value(red1, idx, mk, knn + 1)[0].cpu().numpy()
+    frac = float(mask.float().mean())
+    assert 0.05 < frac < 0.95, frac
+    return res
+
+
 def oracle_run(name):
     c, scene, cam, bg, dL, extra = cases.build_inputs(name)
     kw = dict(viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, campos=cam.camera_center,
@@ -134,6 +165,10 @@ def main():
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **ref)
         fwd, bwd = oracle_run(name)
         compare(name, ref, fwd, bwd)
+    for name in cases.TOOLS_CASES:
+        ref = run_reference_tools(refC, name)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **ref)
+        print(f"  [{name}] tools golden:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in ref.items()})
     print("golden written to", out_dir, {f: os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir)})
 
 

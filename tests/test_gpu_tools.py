@@ -1,0 +1,149 @@
+"""GPU: the reduced-3dgs tools around the rasterizer (SH-culling statistics, redundancy score)
+through the drop-in `_C` entry points, against (a) the golden outputs of the reference itself (tests/golden/t1.npz),
+(b) the CPU oracle and (c) the live reference module at a larger size.
+
+Tolerances: integers / masks exact (oracle: except pairs the oracle flags as within rounding of a threshold, because host powf
+and MUFU-based powf differ in the last ulp); floats 2e-5 relative to the array's scale — the reference's own run-to-run noise
+(float atomics) is recorded in the golden as noise_*."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import cases  # noqa: E402
+import refutil  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(HERE, "golden")
+
+
+def _C():
+    from diff_gaussian_rasterization import _C as c
+    return c
+
+
+def _close(a, b, tol, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), what + ": NaN pattern"
+    m = ~np.isnan(a)
+    scale = np.abs(b[m]).max() + 1e-30
+    err = np.abs(a[m] - b[m]).max() / scale
+    assert err <= tol, (what, err)
+
+
+def _run_ours(c, scene, cams, nb, dev="cuda"):
+    C = _C()
+    ct = {k: v.to(dev) for k, v in cases.tools_camera_tensors(cams).items()}
+    sc = scene.to(dev)
+    P, knn = scene.P, c["knn"]
+    out = {}
+    d, v, m = C.calculate_colours_variance(ct["positions"], sc.means3D, sc.opacity, sc.scales, sc.rotations, ct["views"], ct["projs"],
+                                           ct["tanx"], ct["tany"], ct["H"], ct["W"], sc.sh, sc.degrees, 3)
+    out.update(cv_distance=d, cv_variance=v, cv_mean=m)
+    px = C.find_minimum_projected_pixel_size(ct["projs"], ct["inv_projs"], sc.means3D, ct["H"], ct["W"])
+    out["pixel_size"] = px
+    half = px * c["radius_scale"] * torch.sqrt(torch.tensor([3.0], device=dev)) / 2
+    red, mask = C.sphere_ellipsoid_intersection(sc.means3D, sc.scales, sc.rotations, nb.to(dev), half, knn)
+    out.update(half_diagonal=half, redundancy=red, intersection_mask=mask)
+    idx = torch.cat((torch.arange(P, device=dev, dtype=torch.int).view(-1, 1), nb.to(dev)), dim=1)
+    mk = torch.cat((torch.ones((P, 1), device=dev, dtype=torch.bool), mask), dim=1)
+    out["min_redundancy"] = C.allocate_minimum_redundancy_value(red + 1, idx, mk, knn + 1)[0]
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _check(ours, ref, exact_floats=True):
+    for k in ("cv_distance", "cv_variance", "cv_mean"):
+        _close(ours[k], ref[k], 2e-5, k)
+    if exact_floats:
+        assert np.array_equal(ours["pixel_size"], ref["pixel_size"]), "pixel_size is expected bit-identical (same operation order)"
+    _close(ours["pixel_size"], ref["pixel_size"], 1e-6, "pixel_size")
+    assert ours["redundancy"].dtype == np.int32 and ours["intersection_mask"].dtype == np.bool_
+    assert np.array_equal(ours["intersection_mask"], ref["intersection_mask"])
+    assert np.array_equal(ours["redundancy"], ref["redundancy"])
+    assert np.array_equal(ours["min_redundancy"], ref["min_redundancy"])
+
+
+@pytest.mark.parametrize("name", [n for n in cases.TOOLS_CASES if os.path.isfile(os.path.join(GOLD, n + ".npz"))])
+def test_tools_against_reference_goldens(name):
+    c, scene, cams, nb = cases.build_tools_inputs(name)
+    ref = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    _check(_run_ours(c, scene, cams, nb), ref)
+
+
+def test_tools_against_live_reference(refC):
+    if refC is None or not hasattr(refC, "calculate_colours_variance"):
+        pytest.skip("oracle/_ref/_refC.so with the reduced_3dgs entry points not available")
+    sys.path.insert(0, GOLD)
+    import make_golden
+    views = [(640, 360, -6.0), (512, 512, 4.0), (300, 420, 11.0), (640, 360, 0.0)]
+    c, scene, cams, nb = cases.build_tools_inputs("t1", P=60_000, views=views)
+    c["radius_scale"] = 3.0
+    orig = cases.build_tools_inputs
+    try:
+        cases.build_tools_inputs = lambda name: (c, scene, cams, nb)
+        ref = make_golden.run_reference_tools(refC, "t1")
+    finally:
+        cases.build_tools_inputs = orig
+    _check(_run_ours(c, scene, cams, nb), ref)
+
+
+def test_forward_statistics_against_oracle():
+    """touched_pixels / transmittance_sum of gsb_forward_statistics vs the oracle's renderCUDA restatement."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import gs_oracle as O
+    C = _C()
+    c, scene, cams, nb = cases.build_tools_inputs("t1")
+    cam = cams[0]
+    W, H = cam.image_width, cam.image_height
+    tx, ty = math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5)
+    geom = O.preprocess(scene.means3D, scene.scales, 1.0, scene.rotations, scene.opacity, scene.sh, scene.degrees, None, None,
+                        cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H, tx, ty, None)
+    binning = O.bin_and_sort(geom, W, H)
+    img = O.render_forward_stats(geom, binning, np.zeros(3, np.float32), W, H)
+    sc, cd = scene.to("cuda"), cam.to("cuda")
+    touched = torch.empty((scene.P, 1), dtype=torch.int32, device="cuda")
+    tsum = torch.empty((scene.P, 1), dtype=torch.float32, device="cuda")
+    E = torch.empty(0)
+    R, color, radii, *_ = C._forward(torch.zeros(3, device="cuda"), sc.means3D, E, sc.opacity, sc.scales, sc.rotations, 1.0, E,
+                                     cd.world_view_transform, cd.full_proj_transform, tx, ty, H, W, sc.sh, sc.degrees, cd.camera_center,
+                                     False, False, statistics=(touched, tsum))
+    assert np.array_equal(radii.cpu().numpy(), geom["radii"])
+    # a borderline pixel (threshold decision within MUFU rounding) can move the count of the Gaussians on its tile's list
+    t_o, t_g = img["touched_pixels"], touched.cpu().numpy().reshape(-1)
+    if not img["borderline"].any():
+        assert np.array_equal(t_o, t_g)
+    assert (t_o != t_g).sum() <= 4 * img["borderline"].sum()
+    _close(tsum.cpu().numpy().reshape(-1), img["transmittance_sum"].astype(np.float32), 1e-5 if not img["borderline"].any() else 1e-3, "transmittance_sum")
+    assert int(t_g.sum()) > 0 and np.all(t_g[geom["radii"] == 0] == 0)
+
+
+def test_tools_edge_cases():
+    C = _C()
+    dev = "cuda"
+    # no camera sees the point -> 10000; knn = 0; P = 0
+    xyz = torch.tensor([[0.0, 0.0, -50.0], [0.0, 0.0, 0.0]], device=dev)
+    cam = cases.synth.make_camera(64, 48).to(dev)
+    px = C.find_minimum_projected_pixel_size(cam.full_proj_transform[None], cam.full_proj_transform.inverse()[None], xyz,
+                                             torch.tensor([48], dtype=torch.int32, device=dev), torch.tensor([64], dtype=torch.int32, device=dev))
+    assert px.shape == (2, 1) and float(px[0]) == 10000.0 and 0 < float(px[1]) < 1
+    red, mask = C.sphere_ellipsoid_intersection(xyz, torch.ones(2, 3, device=dev), torch.tensor([[1.0, 0, 0, 0]] * 2, device=dev),
+                                                torch.empty((2, 0), dtype=torch.int32, device=dev), torch.ones(2, 1, device=dev), 0)
+    assert red.shape == (2, 1) and int(red.abs().sum()) == 0 and mask.shape == (2, 0)
+    e = torch.empty((0, 3), device=dev)
+    assert C.find_minimum_projected_pixel_size(cam.full_proj_transform[None], cam.full_proj_transform[None], e,
+                                               torch.tensor([48], dtype=torch.int32), torch.tensor([64], dtype=torch.int32)).shape == (0, 1)
+    out = C.allocate_minimum_redundancy_value(torch.tensor([[3], [1]], dtype=torch.int32, device=dev),
+                                              torch.tensor([[0, 1], [1, 0]], dtype=torch.int32, device=dev),
+                                              torch.tensor([[True, True], [True, False]], device=dev), 2)[0]
+    assert out.cpu().tolist() == [[2], [1]]          # initial value P = 2 caps index 0; index 1 takes min(3, 1)
+    with pytest.raises(RuntimeError):
+        C.calculate_colours_variance(torch.zeros(1, 3, device=dev), torch.zeros(4, 3, device=dev), torch.zeros(4, 1, device=dev),
+                                     torch.ones(4, 3, device=dev), torch.ones(4, 4, device=dev), torch.eye(4, device=dev)[None],
+                                     torch.eye(4, device=dev)[None], torch.ones(1), torch.ones(1), torch.tensor([8]), torch.tensor([8]),
+                                     torch.zeros(4, 16, 3, device=dev), torch.zeros(4, 1, dtype=torch.int32, device=dev), 2)
