@@ -199,6 +199,15 @@ GSB_API int gsb_sphere_ellipsoid_intersection(int32_t P, const float* means3D, c
 GSB_API int gsb_min_redundancy_value(int32_t P, const int32_t* redundancy_values, const int32_t* neighbours, const uint8_t* intersection_mask,
                 int32_t knn, int32_t* minimum_redundancy_values /* [P] */, void* stream);
 
+/* 1-D k-means of the codebook quantisation (Reduced3DGS::kmeans, reduced_3dgs.cu:289-338 + reduced_3dgs/kmeans.cu):
+ * Lloyd iterations from centers_in until sum|old - new| < tol or max_iterations, then ids[i] = index of the nearest centre
+ * (smallest sqrt((c - v)^2), first index on ties).  ids: int32 [n_values]; centers_out: float [n_centers] (n_centers <= 1024;
+ * the reference supports exactly 256).  workspace: gsb_kmeans_workspace_bytes(n_values, n_centers) bytes of device memory.
+ * Synchronises the stream every 16 iterations (the reference: every iteration). */
+GSB_API size_t gsb_kmeans_workspace_bytes(int64_t n_values, int32_t n_centers);
+GSB_API int gsb_kmeans(const float* values, int64_t n_values, const float* centers_in, int32_t n_centers, float tol, int32_t max_iterations,
+                int32_t* ids, float* centers_out, char* workspace, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 GSB_API uint64_t gsb_launch_count(void);
 

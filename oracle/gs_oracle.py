@@ -264,6 +264,39 @@ def min_redundancy_value(redundancy_values, neighbours, intersection_mask, knn):
     return out
 
 
+def kmeans_update_ids(values, centers):
+    """reduced_3dgs/kmeans.cu:70-107 updateIdsCUDA: argmin_i sqrt((c_i - v)^2) in fp32, first index on ties."""
+    v = _np(values, np.float32).reshape(-1)
+    c = _np(centers, np.float32).reshape(-1)
+    ids = np.empty(v.shape[0], np.int32)
+    for a in range(0, v.shape[0], 1 << 16):
+        d = c[None, :] - v[a:a + (1 << 16), None]
+        d = np.sqrt(d * d)
+        d = np.where(np.isnan(d), np.float32(np.inf), d)      # `dist < min_dist` is false for NaN
+        ids[a:a + (1 << 16)] = np.argmin(d, axis=1)
+    return ids
+
+
+def kmeans(values, centers, tol, max_iterations):
+    """Reduced3DGS::kmeans (reduced_3dgs.cu:289-338).  The cluster sums are taken in double (the reference adds floats with
+    atomics in arbitrary order).  Returns (ids int32 [n,1], centers float32 [k], iterations)."""
+    v = _np(values, np.float32).reshape(-1)
+    new = _np(centers, np.float32).reshape(-1).copy()
+    K = new.shape[0]
+    it = 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for it in range(1, max_iterations + 1):
+            ids = kmeans_update_ids(v, new)
+            old = new.copy()
+            sums = np.bincount(ids, weights=v.astype(np.float64), minlength=K).astype(np.float32)
+            sizes = np.bincount(ids, minlength=K).astype(np.float32)
+            new = (sums / sizes).astype(np.float32)
+            new[np.isnan(new)] = 0
+            if np.abs(old - new).sum(dtype=np.float32) < tol:
+                break
+    return kmeans_update_ids(v, new).reshape(-1, 1), new, it
+
+
 def forward(means3D, opacities, scales=None, rotations=None, shs=None, degrees=None, colors_precomp=None,
             cov3D_precomp=None, *, viewmatrix, projmatrix, campos, bg, W, H, tan_fovx, tan_fovy, scale_modifier=1.0,
             packed=None, prune_mask=None):

@@ -62,6 +62,8 @@ int launch_sh_stats_update(int, int, const int*, const float*, const float*, con
 int launch_pixel_size(int, const float*, int, const float*, const float*, const int*, const int*, float*, cudaStream_t);
 int launch_sphere_ellipsoid(int, const float*, const float*, const float*, const int*, const float*, int, int*, uint8_t*, cudaStream_t);
 int launch_min_redundancy(int, const int*, const int*, const uint8_t*, int, int*, cudaStream_t);
+size_t kmeans_workspace_bytes(long long, int);
+int launch_kmeans(const float*, long long, const float*, int, float, int, int*, float*, char*, cudaStream_t);
 int launch_render_backward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, const float*, float*, cudaStream_t);
 int launch_preprocess_backward(const GsbScene*, const GsbCamera*, const GeomState&, const int32_t*, const float*, const GsbGrads*, float, cudaStream_t);
 
@@ -227,6 +229,17 @@ int gsb_sphere_ellipsoid_intersection(int32_t P, const float* means3D, const flo
 	if (P > 0 && (!means3D || !scales || !rotations || !sphere_radius || !redundancy_values || (knn > 0 && (!neighbours || !intersection_mask))))
 	{ set_error("sphere_ellipsoid_intersection: NULL argument"); return GSB_EINVAL; }
 	return launch_sphere_ellipsoid(P, means3D, scales, rotations, neighbours, sphere_radius, knn, redundancy_values, intersection_mask, (cudaStream_t)stream);
+}
+
+size_t gsb_kmeans_workspace_bytes(int64_t n_values, int32_t n_centers) { return kmeans_workspace_bytes(n_values, n_centers); }
+
+int gsb_kmeans(const float* values, int64_t n_values, const float* centers_in, int32_t n_centers, float tol, int32_t max_iterations,
+	int32_t* ids, float* centers_out, char* workspace, void* stream)
+{
+	if (n_values < 0 || n_centers <= 0 || max_iterations < 0) { set_error("kmeans: bad sizes"); return GSB_EINVAL; }
+	if (!centers_in || !centers_out || (n_values > 0 && (!values || !ids || !workspace))) { set_error("kmeans: NULL argument"); return GSB_EINVAL; }
+	if (n_values >= (1ll << 31)) { set_error("kmeans: more than 2^31 values"); return GSB_ERANGE; }
+	return launch_kmeans(values, n_values, centers_in, n_centers, tol, max_iterations, ids, centers_out, workspace, (cudaStream_t)stream);
 }
 
 int gsb_min_redundancy_value(int32_t P, const int32_t* redundancy_values, const int32_t* neighbours, const uint8_t* intersection_mask,

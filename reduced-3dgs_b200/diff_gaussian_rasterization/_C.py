@@ -274,6 +274,23 @@ def allocate_minimum_redundancy_value(redundancy_values, neighbours_indices, int
     return (out,)
 
 
+def kmeans_cuda(values, centers, tol, max_iterations):
+    """reduced_3dgs.h:21-26 Reduced3DGS::kmeans (reduced_3dgs.cu:289-338) -> (ids int32 [n,1], centers float32 [k]).
+    `values` is the [n,1] column of one attribute, `centers` the [k] initial centres (gaussian_model.py:36-41)."""
+    device = _device_of(values)
+    L = _lib.lib()
+    v = f32(values, device)
+    c = f32(centers, device)
+    n, k = int(values.size(0)), int(centers.size(0))
+    ids = torch.zeros((n, 1), dtype=torch.int32, device=device)
+    out = torch.empty((k,), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        ws = torch.empty(int(L.gsb_kmeans_workspace_bytes(n, k)), dtype=torch.uint8, device=device)
+        _lib.check(L.gsb_kmeans(ptr(v.reshape(-1)) if n else None, n, ptr(c.reshape(-1)), k, float(tol), int(max_iterations),
+                                ptr(ids), out.data_ptr(), ws.data_ptr(), _lib.current_stream(device)))
+    return ids, out
+
+
 def mark_visible(means3D, viewmatrix, projmatrix):
     """rasterize_points.h:90-93 markVisible -> bool[P]."""
     device = _device_of(means3D)

@@ -98,3 +98,26 @@ def tools_camera_tensors(cams):
         tany=torch.tensor([math.tan(c.FoVy * 0.5) for c in cams], dtype=torch.float32),
         H=torch.tensor([c.image_height for c in cams], dtype=torch.int32),
         W=torch.tensor([c.image_width for c in cams], dtype=torch.int32))
+
+
+# ---- codebook k-means --------------------------------------------------------------------------
+# n is a multiple of 256 on purpose: in the reference's updateIdsCUDA the threads of the last, partial block return BEFORE they
+# load their share of the centres into shared memory (kmeans.cu:81-91), so for n % 256 != 0 the last n % 256 ids are computed
+# against partly uninitialised shared memory (observed on B200: 41 of the last 64 ids wrong for n = 40 000) — undefined
+# behaviour that is not reproduced here; the tests compare those trailing values only against the oracle.
+KMEANS_CASES = {"k1": dict(n=40_960, zeros=4_096, k=256, seed=31, tol=1e-4, max_iterations=500)}
+
+
+def build_kmeans_inputs(name, n=None):
+    """values ~ N(0,1) with a block of exact zeros and repeated values (culled SH coefficients are exact zeros in the reference),
+    initial centres sampled from the values as generate_codebook does (gaussian_model.py:36-39)."""
+    c = dict(KMEANS_CASES[name])
+    if n is not None:
+        c["n"], c["zeros"] = n, n // 10
+    g = torch.Generator().manual_seed(c["seed"])
+    v = torch.randn(c["n"], generator=g)
+    v[torch.randperm(c["n"], generator=g)[: c["zeros"]]] = 0.0
+    v[::7] = v[1::7][: v[::7].shape[0]]                       # exact duplicates
+    v = v.view(-1, 1).contiguous()
+    centers = v[torch.randint(c["n"], (c["k"],), generator=g)].view(-1).contiguous()
+    return c, v, centers

@@ -89,6 +89,20 @@ def run_reference_tools(refC, name):
     return res
 
 
+def run_reference_kmeans(refC, name):
+    c, v, centers = cases.build_kmeans_inputs(name)
+    v, centers = v.cuda(), centers.cuda()
+    ids0, c0 = refC.kmeans_cuda(v, centers, c["tol"], 0)
+    ids1, c1 = refC.kmeans_cuda(v, centers, 0.0, 1)
+    idsf, cf = refC.kmeans_cuda(v, centers, c["tol"], c["max_iterations"])
+    idsf2, cf2 = refC.kmeans_cuda(v, centers, c["tol"], c["max_iterations"])
+    cost = lambda ids, cc: float((v.view(-1) - cc[ids.view(-1).long()]).abs().double().mean())
+    return dict(ids_iter0=ids0.cpu().numpy(), centers_iter0=c0.cpu().numpy(), ids_iter1=ids1.cpu().numpy(), centers_iter1=c1.cpu().numpy(),
+                ids_final=idsf.cpu().numpy(), centers_final=cf.cpu().numpy(), cost_final=np.float64(cost(idsf, cf)),
+                noise_centers_final=np.float32((cf.sort().values - cf2.sort().values).abs().max().item()),
+                noise_cost_final=np.float64(abs(cost(idsf, cf) - cost(idsf2, cf2))))
+
+
 def oracle_run(name):
     c, scene, cam, bg, dL, extra = cases.build_inputs(name)
     kw = dict(viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, campos=cam.camera_center,
@@ -169,6 +183,11 @@ def main():
         ref = run_reference_tools(refC, name)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **ref)
         print(f"  [{name}] tools golden:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in ref.items()})
+    for name in cases.KMEANS_CASES:
+        ref = run_reference_kmeans(refC, name)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **ref)
+        print(f"  [{name}] kmeans golden: cost {float(ref['cost_final']):.6g}, reference run-to-run noise: centres "
+              f"{float(ref['noise_centers_final']):.3g}, cost {float(ref['noise_cost_final']):.3g}")
     print("golden written to", out_dir, {f: os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir)})
 
 

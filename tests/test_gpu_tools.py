@@ -147,3 +147,78 @@ def test_tools_edge_cases():
                                      torch.ones(4, 3, device=dev), torch.ones(4, 4, device=dev), torch.eye(4, device=dev)[None],
                                      torch.eye(4, device=dev)[None], torch.ones(1), torch.ones(1), torch.tensor([8]), torch.tensor([8]),
                                      torch.zeros(4, 16, 3, device=dev), torch.zeros(4, 1, dtype=torch.int32, device=dev), 2)
+
+
+# ---- codebook k-means (reduced_3dgs.cu:289-338) -----------------------------------------------------------------------
+def _kmeans_cost(v, ids, cc):
+    return float(np.abs(v.reshape(-1).astype(np.float64) - cc.astype(np.float64)[ids.reshape(-1)]).mean())
+
+
+def _kmeans_checks(c, v, centers, ref):
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import gs_oracle as O
+    C = _C()
+    vd, cd = v.cuda(), centers.cuda()
+    # (1) zero iterations = the assignment rule alone: exact, centres unchanged
+    ids0, c0 = C.kmeans_cuda(vd, cd, c["tol"], 0)
+    assert ids0.dtype == torch.int32 and tuple(ids0.shape) == (v.shape[0], 1) and tuple(c0.shape) == (c["k"],)
+    assert np.array_equal(c0.cpu().numpy(), centers.numpy())
+    assert np.array_equal(ids0.cpu().numpy(), ref["ids_iter0"])
+    # (2) one iteration: same partition -> same sizes, centres equal up to float summation order
+    ids1, c1 = C.kmeans_cuda(vd, cd, 0.0, 1)
+    assert np.abs(c1.cpu().numpy() - ref["centers_iter1"]).max() <= 2e-6 * (np.abs(ref["centers_iter1"]).max() + 1e-30) + 1e-7
+    mism = (ids1.cpu().numpy() != ref["ids_iter1"]).mean()
+    assert mism <= 1e-4, mism                                    # a value within an ulp of a boundary may flip with the summation order
+    # (3) to convergence: the returned ids are EXACTLY the assignment for the returned centres, and the quantisation cost
+    #     matches the reference's (trajectories differ by summation-order noise, so centres are compared loosely)
+    idsf, cf = C.kmeans_cuda(vd, cd, c["tol"], c["max_iterations"])
+    idsf, cf = idsf.cpu().numpy(), cf.cpu().numpy()
+    assert np.array_equal(idsf.reshape(-1), O.kmeans_update_ids(v.numpy(), cf))
+    cost = _kmeans_cost(v.numpy(), idsf, cf)
+    assert abs(cost - float(ref["cost_final"])) <= max(2e-3 * float(ref["cost_final"]), 4 * float(ref["noise_cost_final"])), (cost, float(ref["cost_final"]))
+    assert np.abs(np.sort(cf) - np.sort(ref["centers_final"])).max() <= max(2e-2, 10 * float(ref["noise_centers_final"]))
+
+
+@pytest.mark.parametrize("name", [n for n in cases.KMEANS_CASES if os.path.isfile(os.path.join(GOLD, n + ".npz"))])
+def test_kmeans_against_reference_goldens(name):
+    c, v, centers = cases.build_kmeans_inputs(name)
+    _kmeans_checks(c, v, centers, dict(np.load(os.path.join(GOLD, name + ".npz"))))
+
+
+def test_kmeans_against_live_reference_and_edges(refC):
+    C = _C()
+    if refC is not None and hasattr(refC, "kmeans_cuda"):
+        sys.path.insert(0, GOLD)
+        import make_golden
+        c, v, centers = cases.build_kmeans_inputs("k1", n=1_500_160)        # multiple of 256: see cases.KMEANS_CASES
+        orig = cases.build_kmeans_inputs
+        try:
+            cases.build_kmeans_inputs = lambda name: (c, v, centers)
+            ref = make_golden.run_reference_kmeans(refC, "k1")
+        finally:
+            cases.build_kmeans_inputs = orig
+        _kmeans_checks(c, v, centers, ref)
+        # n % 256 != 0: the reference's trailing partial block is undefined (cases.KMEANS_CASES); everything before it must agree
+        c2, v2, centers2 = cases.build_kmeans_inputs("k1", n=10_000)
+        ids_ref, _ = refC.kmeans_cuda(v2.cuda(), centers2.cuda(), 0.0, 0)
+        ids_our, _ = C.kmeans_cuda(v2.cuda(), centers2.cuda(), 0.0, 0)
+        full = 10_000 - 10_000 % 256
+        assert torch.equal(ids_ref[:full], ids_our[:full])
+        sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+        import gs_oracle as O
+        assert np.array_equal(ids_our.cpu().numpy().reshape(-1), O.kmeans_update_ids(v2.numpy(), centers2.numpy()))
+    # all centres equal -> the first iteration puts everything into index 0; the empty clusters become 0 (NaN -> 0, reduced_3dgs.cu:323)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import gs_oracle as O2
+    v = torch.linspace(-1, 1, 1000, device="cuda").view(-1, 1)
+    ids, cc = C.kmeans_cuda(v, torch.full((256,), 0.25, device="cuda"), 0.0, 1)
+    assert abs(float(cc[0]) - float(v.mean())) < 1e-6 and float(cc[1:].abs().sum()) == 0.0
+    assert np.array_equal(ids.cpu().numpy().reshape(-1), O2.kmeans_update_ids(v.cpu().numpy(), cc.cpu().numpy()))
+    # ties: a value exactly between two centres takes the lower INDEX (strict `<` in kmeans.cu:96), wherever that centre lies
+    ids, _ = C.kmeans_cuda(torch.tensor([[0.0], [0.0]], device="cuda"), torch.tensor([1.0, -1.0, 5.0], device="cuda"), 0.0, 0)
+    assert ids.view(-1).tolist() == [0, 0]
+    ids, _ = C.kmeans_cuda(torch.tensor([[0.0]], device="cuda"), torch.tensor([5.0, 1.0, -1.0], device="cuda"), 0.0, 0)
+    assert ids.view(-1).tolist() == [1]
+    # empty input
+    ids, cc = C.kmeans_cuda(torch.empty((0, 1), device="cuda"), torch.arange(4, dtype=torch.float32, device="cuda"), 0.1, 5)
+    assert tuple(ids.shape) == (0, 1) and cc.tolist() == [0.0, 1.0, 2.0, 3.0]

@@ -80,3 +80,26 @@ def test_tools_oracle_self_consistency():
     assert np.array_equal(red.reshape(-1), mask.sum(1)) and 0 < mask.mean() < 1
     mn = O.min_redundancy_value(red, nb, mask, c["knn"])
     assert np.all(mn <= xyz.shape[0]) and np.all(mn >= 0)
+
+
+@pytest.mark.parametrize("name", list(cases.KMEANS_CASES))
+def test_kmeans_oracle_against_reference_goldens(name):
+    path = os.path.join(GOLD, name + ".npz")
+    if not os.path.isfile(path):
+        pytest.skip("golden not generated yet")
+    ref = dict(np.load(path))
+    c, v, centers = cases.build_kmeans_inputs(name)
+    assert np.array_equal(O.kmeans_update_ids(v.numpy(), centers.numpy()).reshape(-1, 1), ref["ids_iter0"])
+    ids1, c1, _ = O.kmeans(v.numpy(), centers.numpy(), 0.0, 1)
+    assert np.abs(c1 - ref["centers_iter1"]).max() <= 2e-6 * np.abs(ref["centers_iter1"]).max() + 1e-7
+    idsf, cf, it = O.kmeans(v.numpy(), centers.numpy(), c["tol"], c["max_iterations"])
+    cost = np.abs(v.numpy().reshape(-1).astype(np.float64) - cf.astype(np.float64)[idsf.reshape(-1)]).mean()
+    assert abs(cost - float(ref["cost_final"])) <= max(2e-3 * float(ref["cost_final"]), 4 * float(ref["noise_cost_final"]))
+
+
+def test_kmeans_oracle_properties():
+    c, v, centers = cases.build_kmeans_inputs("k1", n=5000)
+    ids, cc, it = O.kmeans(v.numpy(), centers.numpy(), 1e-4, 100)
+    assert ids.shape == (5000, 1) and cc.shape == (256,) and 1 <= it <= 100
+    d = np.abs(v.numpy().reshape(-1, 1) - cc.reshape(1, -1))
+    assert np.allclose(d[np.arange(5000), ids.reshape(-1)], d.min(1), atol=1e-7)
