@@ -335,3 +335,27 @@ def test_full_size_properties():
     assert 0.7 < vis.mean() < 0.95
     _, _, fwd2 = ours.run_forward(scene, cam, bg)
     assert np.array_equal(fwd2["color"], fwd["color"]) and np.array_equal(fwd2["keys"], keys)
+
+
+def test_quantised_ply_to_fused_render(tmp_path):
+    """a reduced-3dgs quantised PLY loaded straight into the id planes renders, through the fused
+    de-quantising path, exactly what the original quantised model renders (same ids, same centres -> same bits)."""
+    from gs_b200 import ply
+    ours = _ours()
+    W, H = 320, 200
+    scene = synth.make_scene(20_000, 43, mixed_degrees=True, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.03))
+    order = torch.argsort(scene.degrees.view(-1), stable=True)
+    scene = synth.Scene(*[getattr(scene, f)[order].contiguous() for f in ("means3D", "opacity", "scales", "rotations", "sh", "degrees")])
+    q = synth.quantise_scene(scene)
+    path = str(tmp_path / "point_cloud_quantised.ply")
+    ply.save_reduced_ply(path, q)
+    loaded = ply.load_reduced_ply(path, quantised=True, device="cuda")
+    assert loaded.ids_rest.is_cuda and loaded.ids_rest.dtype == torch.uint8
+    cam = synth.make_camera(W, H)
+    bg = torch.tensor([0.0, 0.2, 0.4])
+    deq = q.to("cuda").dequantise()
+    deq_cpu = synth.Scene(*[getattr(deq, f).cpu() for f in ("means3D", "opacity", "scales", "rotations", "sh", "degrees")])
+    _, _, f1 = ours.run_forward(deq_cpu, cam, bg, quant=q)
+    _, _, f2 = ours.run_forward(deq_cpu, cam, bg, quant=loaded)
+    assert f1["num_rendered"] == f2["num_rendered"] and np.array_equal(f1["point_list"], f2["point_list"])
+    assert np.array_equal(f1["color"], f2["color"]) and np.array_equal(f1["n_contrib"], f2["n_contrib"])
