@@ -172,7 +172,10 @@ def build_workload(args, dev, rank, world):
     quant = prune = None
     if name in ("C3", "C4", "C5"):
         quant = synth.quantise_scene(scene, seed=0)
-        scene = quant.dequantise()          # the fp32 tensors the reference sees (load_ply de-quantises once)
+        # the fp32 tensors the reference sees: its load_ply de-quantises ON THE GPU (gaussian_model.py:371-387 + get_scaling /
+        # get_rotation), and CUDA exp / normalize differ from the CPU ones in the last ulp (a handful of radii out of 6 M)
+        dq = quant.to(dev).dequantise()
+        scene = synth.Scene(*[getattr(dq, f).cpu() for f in ("means3D", "opacity", "scales", "rotations", "sh", "degrees")])
     if name == "C4":
         prune = synth.prune_mask(scene.P, 4)
     return name, W, H, scene, quant, prune
