@@ -65,25 +65,40 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 }
 
 // Per tile: turn the per-CTA histograms into exclusive prefixes over CTAs (in place) and emit the tile total.
-// CTA = 32 tiles x 8 CTA-groups: lanes of a warp read 32 consecutive tiles of one histogram row (128-byte segments), each
-// warp scans its own eighth of the rows, the eight partial totals are combined through shared memory.
-__global__ void __launch_bounds__(256) tile_prefix_kernel(uint32_t* __restrict__ cta_count, int ctas, int T, uint32_t* __restrict__ tile_count)
+// CTA = 32 tiles x 32 row-groups: lanes of a warp read 32 consecutive tiles of one histogram row (128-byte segments), warp g
+// owns rows [g*per, (g+1)*per).  The rows of a thread are loaded into registers first (independent loads, all in flight), the
+// 32 group totals are combined through shared memory, and the prefixes are written once: one read and one write of the table.
+#define PREFIX_GROUPS 32
+#define PREFIX_MAXPER 20            // rows per thread: ctas <= 32 * 20 (make_bin_plan caps ctas at 592)
+__global__ void __launch_bounds__(1024) tile_prefix_kernel(uint32_t* __restrict__ cta_count, int ctas, int T, uint32_t* __restrict__ tile_count)
 {
-	__shared__ uint32_t s_part[8][32];
+	__shared__ uint32_t s_part[PREFIX_GROUPS][32];
 	const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
 	const int t = blockIdx.x * 32 + lane;
-	const int per = (ctas + 7) / 8, c0 = grp * per, c1 = min(ctas, c0 + per);
+	const int per = (ctas + PREFIX_GROUPS - 1) / PREFIX_GROUPS, c0 = grp * per;
+	uint32_t v[PREFIX_MAXPER];
 	uint32_t run = 0;
-	if (t < T)
-		for (int c = c0; c < c1; c++) { const uint32_t v = cta_count[(size_t)c * T + t]; cta_count[(size_t)c * T + t] = run; run += v; }
+#pragma unroll
+	for (int k = 0; k < PREFIX_MAXPER; k++)
+	{
+		const int c = c0 + k;
+		v[k] = (t < T && k < per && c < ctas) ? cta_count[(size_t)c * T + t] : 0u;
+	}
+#pragma unroll
+	for (int k = 0; k < PREFIX_MAXPER; k++) run += v[k];
 	s_part[grp][lane] = run;
 	__syncthreads();
 	uint32_t off = 0, total = 0;
 #pragma unroll
-	for (int g = 0; g < 8; g++) { const uint32_t v = s_part[g][lane]; if (g < grp) off += v; total += v; }
+	for (int g = 0; g < PREFIX_GROUPS; g++) { const uint32_t x = s_part[g][lane]; if (g < grp) off += x; total += x; }
 	if (t < T)
 	{
-		if (off) for (int c = c0; c < c1; c++) cta_count[(size_t)c * T + t] += off;
+#pragma unroll
+		for (int k = 0; k < PREFIX_MAXPER; k++)
+		{
+			const int c = c0 + k;
+			if (k < per && c < ctas) { cta_count[(size_t)c * T + t] = off; off += v[k]; }
+		}
 		if (grp == 0) tile_count[t] = total;
 	}
 }
@@ -105,7 +120,7 @@ __device__ __forceinline__ void st_u64_policy(uint64_t* p, uint64_t v, uint64_t 
 
 // Scatter with privatised cursors: CTA c (same Gaussian chunk as in the preprocess kernel) starts every tile's cursor at
 // tile start + (instances of that tile owned by CTAs < c); slots are then claimed with shared-memory atomics only.
-__global__ void __launch_bounds__(256) scatter_priv_kernel(int P, int chunk, int T, const float4* __restrict__ rec, const uint2* __restrict__ rect,
+__global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk, int T, const float4* __restrict__ rec, const uint2* __restrict__ rect,
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ cta_base, int gx, uint64_t* __restrict__ bucket)
 {
 	extern __shared__ uint32_t s_cur[];
@@ -482,7 +497,7 @@ int launch_tile_scan(const ImageState& img, const GeomState& g, const BinPlan& p
 	ProfScope prof(K_SCAN, stream);
 	if (plan.priv)
 	{
-		tile_prefix_kernel<<<(T + 31) / 32, 256, 0, stream>>>(img.cta_count, plan.ctas, T, img.tile_count);
+		tile_prefix_kernel<<<(T + 31) / 32, 1024, 0, stream>>>(img.cta_count, plan.ctas, T, img.tile_count);
 		GSB_LAUNCHED();
 	}
 	tile_scan_kernel<<<1, 1024, 0, stream>>>(img.tile_count, T, img.ranges, g.counters, img.tile_cursor, img.cls_list, img.cls_count);
@@ -502,7 +517,7 @@ int launch_binning(const GeomState& g, const BinningState& b, const ImageState& 
 		{
 			static bool attr = false;
 			if (!attr) { GSB_CUDA_OK(cudaFuncSetAttribute(scatter_priv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); attr = true; }
-			scatter_priv_kernel<<<plan.ctas, 256, plan.hist_bytes, stream>>>(P, plan.chunk, T, g.rec, g.rect, img.ranges, img.cta_count, gx, b.bucket);
+			scatter_priv_kernel<<<plan.ctas, plan.threads, plan.hist_bytes, stream>>>(P, plan.chunk, T, g.rec, g.rect, img.ranges, img.cta_count, gx, b.bucket);
 		}
 		else
 			scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, img.ranges, img.tile_cursor, gx, b.bucket);

@@ -85,7 +85,7 @@ __device__ __forceinline__ void sh_to_rgb(int deg, float x, float y, float z, SH
 
 
 template <bool QUANT>
-__global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a)
+__global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreArgs a)
 {
 	extern __shared__ float s_cb[];   // QUANT: [20][256] centres; scaling row holds exp(centre)
 	if (QUANT)
@@ -350,8 +350,9 @@ int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& 
 	ProfScope prof(K_PREPROCESS, stream);
 	int grid = plan.priv ? plan.ctas : blocks_needed;
 	if (!plan.priv && a.quant && grid > 148 * 8) grid = 148 * 8;                         // persistent: amortise the table load
-	if (a.quant) preprocess_kernel<true><<<grid, 256, smem, stream>>>(a);
-	else preprocess_kernel<false><<<grid, 256, smem, stream>>>(a);
+	const int threads = plan.priv ? plan.threads : 256;
+	if (a.quant) preprocess_kernel<true><<<grid, threads, smem, stream>>>(a);
+	else preprocess_kernel<false><<<grid, threads, smem, stream>>>(a);
 	GSB_LAUNCHED();
 	GSB_CUDA_OK(cudaGetLastError());
 	return GSB_OK;
