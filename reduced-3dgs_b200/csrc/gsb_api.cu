@@ -54,7 +54,7 @@ int launch_debug_dequant(const GsbQuant*, int, float*, float*, cudaStream_t);
 int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, const ImageState&, const BinPlan&, int32_t*, const GsbDebug*, cudaStream_t);
 int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
 int launch_tile_scan(const ImageState&, const GeomState&, const BinPlan&, int, int, cudaStream_t);
-int launch_binning(const GeomState&, const BinningState&, const ImageState&, const BinPlan&, int, long long, int, int, cudaStream_t);
+int launch_binning(const GeomState&, const BinningState&, const ImageState&, const BinPlan&, int, long long, int, int, uint32_t, uint32_t, cudaStream_t);
 int launch_export_binning(const GeomState&, const BinningState&, const ImageState&, int, int, uint64_t*, uint32_t*, cudaStream_t);
 int launch_render_forward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, float*, int32_t*, float*, cudaStream_t);
 int launch_sh_stats_update(int, int, const int*, const float*, const float*, const float*, const int*, const int*, const float*, float*, float*,
@@ -161,10 +161,10 @@ static int forward_impl(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_f
 	if (!plan.priv) GSB_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, ImageState::tiles(W, H) * sizeof(uint32_t), stream));
 	if (int e = launch_preprocess(scene, cam, g, img, plan, radii, debug, stream)) return e;
 	if (int e = launch_tile_scan(img, g, plan, W, H, stream)) return e;
-	// the instance count sizes the binning blob (rasterizer_impl.cu:445-450): one 16-byte read-back
+	// the instance count sizes the binning blob (rasterizer_impl.cu:445-450): one 32-byte read-back (R, error flag, large-tile class sizes)
 	static thread_local uint32_t* h_counters = nullptr;
 	if (!h_counters) GSB_CUDA_OK(cudaMallocHost(&h_counters, 16 * sizeof(uint32_t)));
-	GSB_CUDA_OK(cudaMemcpyAsync(h_counters, g.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	GSB_CUDA_OK(cudaMemcpyAsync(h_counters, g.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	GSB_CUDA_OK(cudaStreamSynchronize(stream));
 	const long long R = h_counters[0];
 	if (h_counters[3]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSB_ECUDA; }
@@ -173,7 +173,7 @@ static int forward_impl(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_f
 	char* bin_blob = binning_alloc(binning_user, gsb_binning_bytes(R));
 	if (!bin_blob) { set_error("binning allocation failed"); return GSB_ENOMEM; }
 	BinningState b = BinningState::carve(bin_blob, R);
-	if (int e = launch_binning(g, b, img, plan, P, R, W, H, stream)) return e;
+	if (int e = launch_binning(g, b, img, plan, P, R, W, H, h_counters[4], h_counters[5], stream)) return e;
 	if (int e = launch_render_forward(img, b, g, W, H, cam->background, out_color, touched_pixels, transmittance, stream)) return e;
 	return GSB_OK;
 }

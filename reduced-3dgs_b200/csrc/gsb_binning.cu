@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 	__shared__ uint32_t s_warp[32];
 	__shared__ uint32_t s_carry;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) { s_carry = 0; cls_count[0] = 0; cls_count[1] = 0; }
+	if (tid == 0) { s_carry = 0; cls_count[0] = 0; cls_count[1] = 0; cls_count[2] = 0; }
 	__syncthreads();
 	for (int base = 0; base < T; base += 1024)
 	{
@@ -61,7 +61,11 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 		if (tid == 1023) s_carry = start + c;
 		__syncthreads();
 	}
-	if (tid == 0) counters[0] = s_carry;            // num_rendered
+	if (tid == 0)
+	{
+		counters[0] = s_carry;                      // num_rendered
+		counters[4] = cls_count[0]; counters[5] = cls_count[1];   // read back with R: the host skips the large-tile launches when both are 0
+	}
 }
 
 // Per tile: turn the per-CTA histograms into exclusive prefixes over CTAs (in place) and emit the tile total.
@@ -205,8 +209,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, const float4* __res
 // Per-tile sort in shared memory: stable LSD radix sort of (depth bits, id) pairs on the 32 depth bits, 8 bits per pass.
 // Warp w owns positions [w*32*ITEMS, (w+1)*32*ITEMS); ranks inside a warp come from match.any, across warps from a
 // per-digit scan of the per-warp counters (the same stable ranking as a onesweep tile, but the whole "array" is the tile).
-// LIST == false: one CTA per tile (blockIdx.x = tile), tiles with more than CAP instances are skipped (they are on a list).
-// LIST == true : persistent CTAs walk the queued tile list.
+// Persistent CTAs walk a queued tile list (LIST is always true now; the one-CTA-per-tile mode is kept for tooling).
 template <int CAP, int THREADS, bool LIST>
 __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
 	uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cls_list, const uint32_t* __restrict__ cls_count)
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restr
 // (some bin > 32 keys) are flagged and handled by the radix kernel below, so the result never depends on the heuristic.
 #define DIST_BINS 2048
 __global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
-	uint32_t* __restrict__ point_list, uint32_t* __restrict__ fallback_flag)
+	uint32_t* __restrict__ point_list, uint32_t* __restrict__ fallback_list, uint32_t* __restrict__ fallback_count)
 {
 	__shared__ uint32_t s_bin[DIST_BINS];
 	__shared__ __align__(16) uint64_t s_out[GSB_SORT_CAP_A];
@@ -350,7 +353,6 @@ __global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __rest
 	const uint32_t tile = blockIdx.x;
 	const uint2 r = ranges[tile];
 	const uint32_t n = r.y - r.x;
-	if (tid == 0) fallback_flag[tile] = 0;
 	if (n == 0 || n > GSB_SORT_CAP_A) return;
 	if (n == 1) { if (tid == 0) point_list[r.x] = (uint32_t)bucket[r.x]; return; }
 	if (tid == 0) { s_min = 0xffffffffu; s_max = 0u; s_big = 0u; }
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __rest
 	}
 	if (__any_sync(0xffffffffu, worst >= 32)) { if (lane == 0) s_big = 1; }
 	__syncthreads();
-	if (s_big) { if (tid == 0) fallback_flag[tile] = 1; return; }
+	if (s_big) { if (tid == 0) fallback_list[atomicAdd(fallback_count, 1u)] = tile; return; }   // queued for the radix kernel
 	// exclusive scan of the 2048 bin counts: thread t owns bins [8t, 8t+8)
 	uint32_t cnt[8], local = 0;
 #pragma unroll
@@ -506,7 +508,8 @@ int launch_tile_scan(const ImageState& img, const GeomState& g, const BinPlan& p
 	return GSB_OK;
 }
 
-int launch_binning(const GeomState& g, const BinningState& b, const ImageState& img, const BinPlan& plan, int P, long long R, int W, int H, cudaStream_t stream)
+int launch_binning(const GeomState& g, const BinningState& b, const ImageState& img, const BinPlan& plan, int P, long long R, int W, int H,
+	uint32_t n_tiles_over_a, uint32_t n_tiles_over_b, cudaStream_t stream)
 {
 	if (R == 0) return GSB_OK;
 	const int gx = (W + GSB_TILE_X - 1) / GSB_TILE_X, gy = (H + GSB_TILE_Y - 1) / GSB_TILE_Y;
@@ -527,24 +530,31 @@ int launch_binning(const GeomState& g, const BinningState& b, const ImageState& 
 	static bool attr_set = false;
 	if (!attr_set)
 	{
-		GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<GSB_SORT_CAP_A, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+		GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<GSB_SORT_CAP_A, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
 		GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<GSB_SORT_CAP_B, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
 		attr_set = true;
 	}
 	{
 		ProfScope prof(K_SORT_PASS, stream);
-		tile_sort_dist_kernel<<<T, 256, 0, stream>>>(img.ranges, b.bucket, b.point_list, img.tile_cursor);   // cursors are dead after the scatter: reused as flags
+		tile_sort_dist_kernel<<<T, 256, 0, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list + 2 * (size_t)T, img.cls_count + 2);
 		GSB_LAUNCHED();
 	}
 	{
 		ProfScope prof(K_SORT_LARGE, stream);
-		tile_sort_kernel<GSB_SORT_CAP_A, 256, false><<<T, 256, smemA, stream>>>(img.ranges, b.bucket, b.point_list, img.tile_cursor, nullptr);
+		// radix fallback for the tiles the distribution sort queued (device-side list; normally empty: the CTAs exit at once)
+		tile_sort_kernel<GSB_SORT_CAP_A, 256, true><<<148 * 4, 256, smemA, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list + 2 * (size_t)T,
+			img.cls_count + 2);
 		GSB_LAUNCHED();
 	}
+	if (n_tiles_over_a)                     // class sizes came back with R: nothing is launched for classes that are empty
 	{
 		ProfScope prof(K_SORT_LARGE, stream);
 		tile_sort_kernel<GSB_SORT_CAP_B, 1024, true><<<148, 1024, smemB, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list, img.cls_count);
 		GSB_LAUNCHED();
+	}
+	if (n_tiles_over_b)
+	{
+		ProfScope prof(K_SORT_LARGE, stream);
 		tile_sort_big_kernel<<<74, 1024, 0, stream>>>(img.ranges, b.bucket, b.alt, b.point_list, img.cls_list + T, img.cls_count + 1);
 		GSB_LAUNCHED();
 	}
