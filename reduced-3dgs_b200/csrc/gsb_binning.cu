@@ -4,19 +4,22 @@
 // R (tile << 32 | depth bits, gaussian id) pairs, ONE global cub::DeviceRadixSort over all R 64-bit keys
 // (6 digit passes = ~150 B of HBM traffic per instance), then identifyTileRanges.
 //
-// What this file does instead — same result, bit for bit, ~20 B per instance:
-//   1. the preprocess kernel already counted the instances of every tile (one RED per (Gaussian, tile));
-//   2. tile_scan_kernel: exclusive scan of the T tile counters -> ranges[t] = (start, end) directly
-//      (== identifyTileRanges' output) and R;
-//   3. scatter_kernel: every (Gaussian, tile) instance claims a slot in its tile's segment with an atomic cursor and
-//      stores the 64-bit composite (depth bits << 32 | gaussian id);
-//   4. tile_sort_kernel: one CTA per tile sorts its segment entirely in shared memory: a stable 8-bit LSD radix sort on the
-//      32 depth bits (digits in which all keys of the tile agree are skipped), then the (rare) runs of bit-identical depths
-//      are put in ascending Gaussian id, and the ids are written -> point_list.
+// What this file does instead — same result, bit for bit, ~20 B of algorithmic traffic per instance, no global atomics:
+//   1. the preprocess kernel counts (Gaussian, tile) pairs into a PER-CTA shared-memory tile histogram; every CTA owns a
+//      contiguous chunk of Gaussians (BinPlan) and flushes its histogram as one row of cta_count[ctas][tiles];
+//   2. tile_prefix_kernel: per tile, exclusive prefix over the CTA rows (in place) + tile totals;
+//      tile_scan_kernel: exclusive scan of the T tile totals -> ranges[t] = (start, end) directly (== identifyTileRanges'
+//      output), R, and the lists of tiles too large for the one-CTA sort classes;
+//   3. scatter_priv_kernel: the same chunking again; slot = tile start + this CTA's prefix + shared-memory cursor; stores the
+//      64-bit composite (depth bits << 32 | gaussian id) with an L2 evict_last policy (sector-complete write-back);
+//   4. tile_sort_dist_kernel: one CTA per tile, one-pass distribution sort (2048 order-preserving depth bins + in-bin
+//      insertion by (depth bits, id)); tiles whose depths cluster are queued on a device-side list for the stable 8-bit LSD
+//      radix sort in shared memory (tile_sort_kernel); tiles above 2048 / 8192 instances go to persistent 1024-thread CTAs /
+//      a single-CTA global-memory radix sort, launched only when those classes are non-empty (sizes ride the R read-back).
 // The global stable sort by (tile, depth) with ties in emission order (ascending Gaussian id) is exactly "per tile, sort
 // by (depth bits, id)": a Gaussian appears at most once per tile, so the composites are unique and the order is total.
-// Segments larger than the shared-memory classes (> 8192 instances in one tile) fall back to a single-CTA global-memory
-// LSD radix sort on the 64-bit composite.
+// When the tile histogram does not fit in shared memory (> 160 KB, i.e. beyond ~8K images) counting and scattering fall
+// back to global atomics (tile_count / scatter_kernel).
 // (The first version of this file was a hand-written 8-bit onesweep radix sort; see git history and DESIGN.md.)
 #include "gsb_common.cuh"
 
