@@ -208,6 +208,21 @@ GSB_API size_t gsb_kmeans_workspace_bytes(int64_t n_values, int32_t n_centers);
 GSB_API int gsb_kmeans(const float* values, int64_t n_values, const float* centers_in, int32_t n_centers, float tol, int32_t max_iterations,
                 int32_t* ids, float* centers_out, char* workspace, void* stream);
 
+/* Loss side of the training step: (1 - lambda) * L1 + lambda * (1 - SSIM) of image vs gt, both [C,H,W] fp32
+ * (reference utils/loss_utils.py:17-65 l1_loss / ssim with the 11x11 sigma-1.5 window and zero padding, combined as in
+ * train.py:110-115).  Forward writes maps [3,C,H,W] (d ssim / d mu_x, E[x^2], E[xy]) and per-CTA partial sums
+ * [gsb_l1_ssim_blocks(C,H,W)][2] = (sum of the SSIM map, sum |x - y|); the caller adds them up:
+ *   ssim = sum(partial[:,0]) / (C H W),  l1 = sum(partial[:,1]) / (C H W).
+ * Backward: dL/dimage = coef_l1 * (*upstream_l1) * d l1/dimage + coef_ssim * (*upstream_ssim) * d ssim/dimage; the upstreams are
+ * DEVICE scalars (NULL = 1), so autograd's incoming gradients are consumed without a host synchronisation.  For the combined
+ * loss (1 - lambda) l1 + lambda (1 - ssim): coef_l1 = 1 - lambda, coef_ssim = -lambda, both upstreams = dL/dloss. */
+GSB_API int64_t gsb_l1_ssim_blocks(int32_t channels, int32_t height, int32_t width);
+GSB_API int gsb_l1_ssim_forward(const float* image, const float* gt, int32_t channels, int32_t height, int32_t width,
+                float* maps, float* partial_sums, void* stream);
+GSB_API int gsb_l1_ssim_backward(const float* image, const float* gt, int32_t channels, int32_t height, int32_t width,
+                const float* maps, float coef_l1, const float* upstream_l1, float coef_ssim, const float* upstream_ssim,
+                float* dL_dimage, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 GSB_API uint64_t gsb_launch_count(void);
 

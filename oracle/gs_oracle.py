@@ -297,6 +297,43 @@ def kmeans(values, centers, tol, max_iterations):
     return kmeans_update_ids(v, new).reshape(-1, 1), new, it
 
 
+def _ssim_window():
+    """gaussian(11, 1.5) of utils/loss_utils.py:23-25 in float32, as float64 array."""
+    import math
+    g = np.array([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)], np.float32)
+    return (g / g.sum(dtype=np.float32)).astype(np.float64)
+
+
+def _sepconv(a, w):
+    """zero-padded 'same' separable correlation of [C,H,W] with the 11-tap window along H and W (== conv2d(padding=5, groups=C))."""
+    C, H, W = a.shape
+    p = np.zeros((C, H + 10, W + 10), np.float64)
+    p[:, 5:5 + H, 5:5 + W] = a
+    t = sum(w[k] * p[:, :, k:k + W] for k in range(11))
+    return sum(w[k] * t[:, k:k + H, :] for k in range(11))
+
+
+def l1_ssim(image, gt, lambda_dssim=0.2):
+    """utils/loss_utils.py:17-18 l1_loss, :33-65 ssim / _ssim and their combination of train.py:110-115, in float64, with the
+    analytic gradient of the combined loss w.r.t. `image`.  Returns (l1, ssim, loss, dloss_dimage)."""
+    x, y = _np(image, np.float64), _np(gt, np.float64)
+    w = _ssim_window()
+    N = x.size
+    mu1, mu2 = _sepconv(x, w), _sepconv(y, w)
+    exx, eyy, exy = _sepconv(x * x, w), _sepconv(y * y, w), _sepconv(x * y, w)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    A1, A2 = 2 * mu1 * mu2 + C1, 2 * (exy - mu1 * mu2) + C2
+    B1, B2 = mu1 ** 2 + mu2 ** 2 + C1, (exx - mu1 ** 2) + (eyy - mu2 ** 2) + C2
+    smap = A1 * A2 / (B1 * B2)
+    l1, ssim = np.abs(x - y).mean(), smap.mean()
+    d_mu = 2 * mu2 * (A2 - A1) / (B1 * B2) - smap * 2 * mu1 * (B2 - B1) / (B1 * B2)
+    d_xx = -smap / B2
+    d_xy = 2 * A1 / (B1 * B2)
+    dssim = (_sepconv(d_mu, w) + 2 * x * _sepconv(d_xx, w) + y * _sepconv(d_xy, w)) / N
+    grad = (1 - lambda_dssim) * np.sign(x - y) / N - lambda_dssim * dssim
+    return l1, ssim, (1 - lambda_dssim) * l1 + lambda_dssim * (1 - ssim), grad
+
+
 def forward(means3D, opacities, scales=None, rotations=None, shs=None, degrees=None, colors_precomp=None,
             cov3D_precomp=None, *, viewmatrix, projmatrix, campos, bg, W, H, tan_fovx, tan_fovy, scale_modifier=1.0,
             packed=None, prune_mask=None):

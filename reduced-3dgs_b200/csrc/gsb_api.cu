@@ -62,6 +62,8 @@ int launch_sh_stats_update(int, int, const int*, const float*, const float*, con
 int launch_pixel_size(int, const float*, int, const float*, const float*, const int*, const int*, float*, cudaStream_t);
 int launch_sphere_ellipsoid(int, const float*, const float*, const float*, const int*, const float*, int, int*, uint8_t*, cudaStream_t);
 int launch_min_redundancy(int, const int*, const int*, const uint8_t*, int, int*, cudaStream_t);
+int launch_l1_ssim_forward(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+int launch_l1_ssim_backward(const float*, const float*, int, int, int, const float*, float, const float*, float, const float*, float*, cudaStream_t);
 size_t kmeans_workspace_bytes(long long, int);
 int launch_kmeans(const float*, long long, const float*, int, float, int, int*, float*, char*, cudaStream_t);
 int launch_render_backward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, const float*, float*, cudaStream_t);
@@ -229,6 +231,26 @@ int gsb_sphere_ellipsoid_intersection(int32_t P, const float* means3D, const flo
 	if (P > 0 && (!means3D || !scales || !rotations || !sphere_radius || !redundancy_values || (knn > 0 && (!neighbours || !intersection_mask))))
 	{ set_error("sphere_ellipsoid_intersection: NULL argument"); return GSB_EINVAL; }
 	return launch_sphere_ellipsoid(P, means3D, scales, rotations, neighbours, sphere_radius, knn, redundancy_values, intersection_mask, (cudaStream_t)stream);
+}
+
+int64_t gsb_l1_ssim_blocks(int32_t channels, int32_t height, int32_t width)
+{
+	return (int64_t)channels * ((height + 15) / 16) * ((width + 15) / 16);
+}
+
+int gsb_l1_ssim_forward(const float* image, const float* gt, int32_t channels, int32_t height, int32_t width, float* maps, float* partial_sums,
+	void* stream)
+{
+	if (channels <= 0 || height <= 0 || width <= 0 || !image || !gt || !maps || !partial_sums) { set_error("l1_ssim_forward: bad arguments"); return GSB_EINVAL; }
+	return launch_l1_ssim_forward(image, gt, channels, height, width, maps, partial_sums, (cudaStream_t)stream);
+}
+
+int gsb_l1_ssim_backward(const float* image, const float* gt, int32_t channels, int32_t height, int32_t width, const float* maps,
+	float coef_l1, const float* upstream_l1, float coef_ssim, const float* upstream_ssim, float* dL_dimage, void* stream)
+{
+	if (channels <= 0 || height <= 0 || width <= 0 || !image || !gt || !maps || !dL_dimage) { set_error("l1_ssim_backward: bad arguments"); return GSB_EINVAL; }
+	return launch_l1_ssim_backward(image, gt, channels, height, width, maps, coef_l1, upstream_l1, coef_ssim, upstream_ssim, dL_dimage,
+		(cudaStream_t)stream);
 }
 
 size_t gsb_kmeans_workspace_bytes(int64_t n_values, int32_t n_centers) { return kmeans_workspace_bytes(n_values, n_centers); }

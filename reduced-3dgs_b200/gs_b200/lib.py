@@ -108,6 +108,13 @@ def lib():
         L.gsb_kmeans.restype = C.c_int
         L.gsb_kmeans.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]
+        L.gsb_l1_ssim_blocks.restype = C.c_int64
+        L.gsb_l1_ssim_blocks.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.gsb_l1_ssim_forward.restype = C.c_int
+        L.gsb_l1_ssim_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gsb_l1_ssim_backward.restype = C.c_int
+        L.gsb_l1_ssim_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_float, C.c_void_p,
+                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gsb_backward.restype = C.c_int
         L.gsb_backward.argtypes = [C.POINTER(GsbScene), C.POINTER(GsbCamera), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(GsbGrads), C.c_float, C.c_void_p]
@@ -146,7 +153,8 @@ EXPORTED_SYMBOLS = ["gsb_geom_bytes", "gsb_image_bytes", "gsb_binning_bytes", "g
                     "gsb_mark_visible", "gsb_export_binning", "gsb_export_image", "gsb_launch_count", "gsb_last_error",
                     "gsb_version", "gsb_profile_enable", "gsb_profile_read", "gsb_debug_dequant", "gsb_forward_statistics",
                     "gsb_sh_statistics_update", "gsb_min_projected_pixel_size", "gsb_sphere_ellipsoid_intersection",
-                    "gsb_min_redundancy_value", "gsb_kmeans_workspace_bytes", "gsb_kmeans"]
+                    "gsb_min_redundancy_value", "gsb_kmeans_workspace_bytes", "gsb_kmeans", "gsb_l1_ssim_blocks",
+                    "gsb_l1_ssim_forward", "gsb_l1_ssim_backward"]
 
 
 def check(status: int):

@@ -222,3 +222,37 @@ def test_kmeans_against_live_reference_and_edges(refC):
     # empty input
     ids, cc = C.kmeans_cuda(torch.empty((0, 1), device="cuda"), torch.arange(4, dtype=torch.float32, device="cuda"), 0.1, 5)
     assert tuple(ids.shape) == (0, 1) and cc.tolist() == [0.0, 1.0, 2.0, 3.0]
+
+
+# ---- loss side of the step: L1 + D-SSIM (utils/loss_utils.py, train.py:110-115) --------------------------------------------
+def test_loss_against_reference_golden_and_oracle():
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import gs_oracle as O
+    import make_golden_loss as M
+    from utils import loss_utils as LU
+    ref = dict(np.load(os.path.join(GOLD, "loss1.npz")))
+    img, gt = M.inputs()
+    lam = float(ref["lambda_dssim"])
+    x = img.cuda().requires_grad_(True)
+    loss = LU.l1_ssim_loss(x, gt.cuda(), lam)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref["loss"])) < 2e-6
+    assert np.abs(x.grad.cpu().numpy() - ref["grad"]).max() <= 2e-4 * np.abs(ref["grad"]).max()
+    # the reference's call pattern: two functions, combined by autograd (train.py:110-115)
+    x2 = img.cuda().requires_grad_(True)
+    Ll1, s = LU.l1_loss(x2, gt.cuda()), LU.ssim(x2, gt.cuda())
+    assert abs(float(Ll1.detach()) - float(ref["l1"])) < 1e-7 and abs(float(s.detach()) - float(ref["ssim"])) < 2e-5
+    ((1.0 - lam) * Ll1 + lam * (1.0 - s)).backward()
+    assert np.abs(x2.grad.cpu().numpy() - ref["grad"]).max() <= 2e-4 * np.abs(ref["grad"]).max()
+    x3 = img.cuda().requires_grad_(True)
+    LU.ssim(x3, gt.cuda()).backward()
+    assert np.abs(x3.grad.cpu().numpy() - ref["grad_ssim_only"]).max() <= 2e-4 * np.abs(ref["grad_ssim_only"]).max()
+    # full size, non-trivial upstream gradient, against the float64 oracle
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(3, 1080, 1920, generator=g), torch.rand(3, 1080, 1920, generator=g)
+    xa = a.cuda().requires_grad_(True)
+    (2.5 * LU.l1_ssim_loss(xa, b.cuda(), 0.2)).backward()
+    l1, ss, lo, gr = O.l1_ssim(a, b, 0.2)
+    assert np.abs(xa.grad.cpu().numpy() - 2.5 * gr).max() <= 1e-4 * np.abs(2.5 * gr).max()
+    with pytest.raises(NotImplementedError):
+        LU.ssim(x, gt.cuda(), window_size=7)

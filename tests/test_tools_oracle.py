@@ -103,3 +103,16 @@ def test_kmeans_oracle_properties():
     assert ids.shape == (5000, 1) and cc.shape == (256,) and 1 <= it <= 100
     d = np.abs(v.numpy().reshape(-1, 1) - cc.reshape(1, -1))
     assert np.allclose(d[np.arange(5000), ids.reshape(-1)], d.min(1), atol=1e-7)
+
+
+def test_loss_oracle_against_reference_golden():
+    """oracle.l1_ssim (float64, analytic gradient) vs the reference's own utils/loss_utils.py + autograd (tests/golden/loss1.npz,
+    written by tests/golden/make_golden_loss.py by importing /root/reference on CPU)."""
+    import make_golden_loss as M
+    ref = dict(np.load(os.path.join(GOLD, "loss1.npz")))
+    img, gt = M.inputs()
+    l1, ss, loss, grad = O.l1_ssim(img, gt, float(ref["lambda_dssim"]))
+    assert abs(l1 - float(ref["l1"])) < 1e-7 and abs(ss - float(ref["ssim"])) < 2e-5 and abs(loss - float(ref["loss"])) < 1e-5
+    assert np.abs(grad - ref["grad"]).max() <= 2e-4 * np.abs(ref["grad"]).max()
+    _, _, _, g_ssim = O.l1_ssim(img, gt, 1.0)                      # loss = 1 - ssim  ->  d ssim = -grad
+    assert np.abs(-g_ssim - ref["grad_ssim_only"]).max() <= 2e-4 * np.abs(ref["grad_ssim_only"]).max()
