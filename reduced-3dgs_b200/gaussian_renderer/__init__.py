@@ -8,8 +8,13 @@ Build-defined extras: `pc.prune_mask` (optional tensor) and `pc.quant` (optional
 fused kernels when present.
 """
 import math
+import pkgutil
 
 import torch
+
+# When this package shadows the reference's `gaussian_renderer` on sys.path, its sibling modules (network_gui, imported by
+# train.py next to `render`) must stay importable: let submodule lookups continue into same-named packages further down the path.
+__path__ = pkgutil.extend_path(__path__, __name__)
 
 from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
 from diff_gaussian_rasterization._C import rasterize_gaussians_variableSH_bands
