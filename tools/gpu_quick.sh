@@ -1,2 +1,11 @@
-timeout 900 python -m pytest tests/test_gpu_tools.py -x -q -k loss 2>&1 | tail -12
-timeout 600 python tools/bench_loss.py 2>&1 | tail -3
+# quick GPU check: full gpu test-suite + device-resident bench at C2 / C3
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for c in C2 C3; do
+timeout 600 python bench.py --config $c --no-cpu-baseline --no-e2e > gpurun_out/b_$c.json 2> gpurun_out/b_$c.err
+done
+python - <<'PY'
+import json
+for c in ['C2','C3']:
+    d=json.loads(open(f'gpurun_out/b_{c}.json').read().strip().splitlines()[-1])
+    print(c, d['value'], d['ms_per_step'], d['step_ms'], d['config'].get('instances_R'), {k:round(v['ms_per_step'],3) for k,v in d['roofline']['kernels'].items()})
+PY
