@@ -128,11 +128,14 @@ __device__ __forceinline__ void st_u64_policy(uint64_t* p, uint64_t v, uint64_t 
 // Scatter with privatised cursors: CTA c (same Gaussian chunk as in the preprocess kernel) starts every tile's cursor at
 // tile start + (instances of that tile owned by CTAs < c); slots are then claimed with shared-memory atomics only.
 __global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk, int T, const float4* __restrict__ rec, const uint2* __restrict__ rect,
-	const uint2* __restrict__ ranges, const uint32_t* __restrict__ cta_base, int gx, uint64_t* __restrict__ bucket)
+	const uint2* __restrict__ ranges, const uint32_t* __restrict__ cta_base, int gx, uint32_t y_lo, uint32_t y_hi, uint64_t* __restrict__ bucket)
 {
+	// One launch handles the tile rows [y_lo, y_hi): when the bucket array is larger than L2 the host splits the image into row
+	// bands whose slice of the (tile-major) array fits, so that the scattered 8-byte stores still complete their sectors in L2.
 	extern __shared__ uint32_t s_cur[];
 	const uint32_t* base = cta_base + (size_t)blockIdx.x * T;
-	for (int t = threadIdx.x; t < T; t += blockDim.x) s_cur[t] = ranges[t].x + base[t];
+	const int t0 = (int)y_lo * gx, nt = (int)(y_hi - y_lo) * gx;
+	for (int t = threadIdx.x; t < nt; t += blockDim.x) s_cur[t] = ranges[t0 + t].x + base[t0 + t];
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
 	const uint64_t pol = l2_policy_evict_last();
@@ -146,14 +149,15 @@ __global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk,
 			rc = __ldcs(&rect[idx]);
 			if (rc.x | rc.y) dbits = __float_as_uint(__ldcs(&rec[3 * (size_t)idx + 2]).z);
 		}
-		const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16, miny = rc.y & 0xffffu, maxy = rc.y >> 16;
-		const uint32_t w = maxx - minx, t = w * (maxy - miny);
+		const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16;
+		const uint32_t miny = max(rc.y & 0xffffu, y_lo), maxy = min(rc.y >> 16, y_hi);       // clipped to this band
+		const uint32_t w = maxx - minx, t = maxy > miny ? w * (maxy - miny) : 0u;
 		const bool big = t > 32;
 		if (t && !big)
 		{
 			const uint64_t comp = ((uint64_t)dbits << 32) | (uint32_t)idx;
 			for (uint32_t y = miny; y < maxy; y++)
-				for (uint32_t x = minx; x < maxx; x++) st_u64_policy(&bucket[atomicAdd(&s_cur[y * gx + x], 1u)], comp, pol);
+				for (uint32_t x = minx; x < maxx; x++) st_u64_policy(&bucket[atomicAdd(&s_cur[(y - y_lo) * gx + x], 1u)], comp, pol);
 		}
 		unsigned bigmask = __ballot_sync(0xffffffffu, big);
 		while (bigmask)
@@ -162,7 +166,8 @@ __global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk,
 			const uint32_t bt = __shfl_sync(0xffffffffu, t, src), bw = __shfl_sync(0xffffffffu, w, src);
 			const uint32_t bminx = __shfl_sync(0xffffffffu, minx, src), bminy = __shfl_sync(0xffffffffu, miny, src);
 			const uint64_t comp = ((uint64_t)__shfl_sync(0xffffffffu, dbits, src) << 32) | (uint32_t)(idx - lane + src);
-			for (uint32_t k = lane; k < bt; k += 32) st_u64_policy(&bucket[atomicAdd(&s_cur[(bminy + k / bw) * gx + bminx + k % bw], 1u)], comp, pol);
+			for (uint32_t k = lane; k < bt; k += 32)
+				st_u64_policy(&bucket[atomicAdd(&s_cur[(bminy - y_lo + k / bw) * gx + bminx + k % bw], 1u)], comp, pol);
 		}
 	}
 }
@@ -523,7 +528,16 @@ int launch_binning(const GeomState& g, const BinningState& b, const ImageState& 
 		{
 			static bool attr = false;
 			if (!attr) { GSB_CUDA_OK(cudaFuncSetAttribute(scatter_priv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); attr = true; }
-			scatter_priv_kernel<<<plan.ctas, plan.threads, plan.hist_bytes, stream>>>(P, plan.chunk, T, g.rec, g.rect, img.ranges, img.cta_count, gx, b.bucket);
+			// row bands: each band's slice of the bucket array (8 B x its instances, tile-major = contiguous) should fit L2
+			const int bands = (int)std::min<long long>(gy, std::max<long long>(1, (R * 8 + (104ll << 20) - 1) / (104ll << 20)));
+			const int rows = (gy + bands - 1) / bands;
+			for (int y0 = 0; y0 < gy; y0 += rows)
+			{
+				const int y1 = std::min(gy, y0 + rows);
+				scatter_priv_kernel<<<plan.ctas, plan.threads, size_t(y1 - y0) * gx * sizeof(uint32_t), stream>>>(P, plan.chunk, T, g.rec, g.rect,
+					img.ranges, img.cta_count, gx, (uint32_t)y0, (uint32_t)y1, b.bucket);
+				if (y0) GSB_LAUNCHED();
+			}
 		}
 		else
 			scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, img.ranges, img.tile_cursor, gx, b.bucket);
