@@ -24,6 +24,8 @@ WANT = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "time"), ("dram__b
 def main(rep, out):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3 or "Kernel Name" not in rows[0]:
+        sys.exit(f"{rep}: no kernels in the report (missing or empty capture) - {out} left untouched")
     hdr, units = rows[0], rows[1]
     idx = [(hdr.index(k), n) for k, n in WANT if k in hdr]
     with open(out, "w", newline="") as f:
