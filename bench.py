@@ -127,27 +127,7 @@ def bench_cameras(W, H, n=16):
     return cams
 
 
-class ModelView:
-    """Duck-typed stand-in for the reference GaussianModel (the attributes gaussian_renderer.render reads)."""
-
-    def __init__(self, scene, dev, quant=None, prune_mask=None):
-        self._xyz = scene.means3D.to(dev).requires_grad_(True)
-        self._opacity = scene.opacity.to(dev).requires_grad_(quant is None)
-        self._scaling = scene.scales.to(dev).requires_grad_(quant is None)
-        self._rotation = scene.rotations.to(dev).requires_grad_(quant is None)
-        self._features = scene.sh.to(dev).requires_grad_(quant is None)
-        self._degrees = scene.degrees.to(dev)
-        self.active_sh_degree = self.max_sh_degree = 3
-        self.quant, self.prune_mask = quant, prune_mask
-        self.per_band_count = [int((scene.degrees == d).sum()) for d in range(4)]
-
-    get_xyz = property(lambda s: s._xyz)
-    get_scaling = property(lambda s: s._scaling)
-    get_rotation = property(lambda s: s._rotation)
-    get_features = property(lambda s: s._features)
-
-    def params(self):
-        return [self._xyz, self._opacity, self._scaling, self._rotation, self._features]
+from gs_b200.model import GaussianModelView as ModelView  # noqa: E402  (the attributes gaussian_renderer.render reads)
 
 
 def algorithmic_bytes(P, V, R, sumK, Npx, Nt, rho_f, rho_b, quant, mask):

@@ -359,3 +359,28 @@ def test_quantised_ply_to_fused_render(tmp_path):
     _, _, f2 = ours.run_forward(deq_cpu, cam, bg, quant=loaded)
     assert f1["num_rendered"] == f2["num_rendered"] and np.array_equal(f1["point_list"], f2["point_list"])
     assert np.array_equal(f1["color"], f2["color"]) and np.array_equal(f1["n_contrib"], f2["n_contrib"])
+
+
+def test_render_from_quantised_ply_through_model_view(tmp_path):
+    """render() on a GaussianModelView built from a quantised PLY == render() on the fp32 model the file was made from
+    (same ids and centres; the fused path de-quantises in the kernel), and == the reference-equivalent fp32 expansion within 1e-4."""
+    from types import SimpleNamespace
+    from gs_b200 import ply
+    from gs_b200.model import GaussianModelView
+    from gaussian_renderer import render
+    W, H = 320, 200
+    scene = synth.make_scene(20_000, 44, mixed_degrees=True, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.03))
+    order = torch.argsort(scene.degrees.view(-1), stable=True)
+    scene = synth.Scene(*[getattr(scene, f)[order].contiguous() for f in ("means3D", "opacity", "scales", "rotations", "sh", "degrees")])
+    q = synth.quantise_scene(scene)
+    path = str(tmp_path / "point_cloud_quantised.ply")
+    ply.save_reduced_ply(path, q)
+    view = GaussianModelView.from_ply(path, quantised=True, device="cuda")
+    cam = synth.make_camera(W, H).to("cuda")
+    pipe = SimpleNamespace(debug=False, convert_SHs_python=False, compute_cov3D_python=False)
+    bg = torch.tensor([0.2, 0.1, 0.0], device="cuda")
+    with torch.no_grad():
+        img_q = render(cam, view, pipe, bg)["render"]
+        img_f = render(cam, GaussianModelView(q.to("cuda").dequantise(), "cuda", requires_grad=False), pipe, bg)["render"]
+    assert float((img_q - img_f).abs().max()) <= 1e-4
+    assert float(img_q.abs().max()) > 0.05

@@ -101,3 +101,20 @@ def test_reader_rejects_what_the_format_does_not_use(tmp_path):
     p.write_bytes(b"plx\n")
     with pytest.raises(ValueError):
         ply.read_ply(str(p))
+
+
+def test_model_view_from_ply(tmp_path):
+    """gs_b200.model.GaussianModelView: the attributes gaussian_renderer.render() reads, built straight from a quantised PLY."""
+    from gs_b200.model import GaussianModelView
+    scene, q = _model(200)
+    path = str(tmp_path / "q.ply")
+    ply.save_reduced_ply(path, q)
+    v = GaussianModelView.from_ply(path, quantised=True, device="cpu")
+    assert v.quant is not None and v.quant.ids_rest.dtype == torch.uint8 and v.num_primitives == 200
+    assert v.per_band_count == [int((scene.degrees == d).sum()) for d in range(4)] and sum(v.per_band_count) == 200
+    assert tuple(v.get_features.shape) == (200, 16, 3) and tuple(v._opacity.shape) == (200, 1) and v._degrees.dtype == torch.int32
+    assert torch.equal(v.get_xyz, q.means3D) and not v.get_xyz.requires_grad
+    d = q.dequantise()
+    assert torch.equal(v.get_scaling, d.scales) and torch.equal(v.get_rotation, d.rotations)
+    t = GaussianModelView(scene, "cpu")                       # trainable fp32 view
+    assert all(p.requires_grad for p in t.params()) and t.quant is None
