@@ -384,3 +384,26 @@ def test_render_from_quantised_ply_through_model_view(tmp_path):
         img_f = render(cam, GaussianModelView(q.to("cuda").dequantise(), "cuda", requires_grad=False), pipe, bg)["render"]
     assert float((img_q - img_f).abs().max()) <= 1e-4
     assert float(img_q.abs().max()) > 0.05
+
+
+def test_global_atomics_binning_path_beyond_shared_memory():
+    """Images with more than 40 960 tiles do not fit the per-CTA shared-memory tile histogram (BinPlan.priv == 0): counting and
+    scattering fall back to global atomics.  Same integer results and image as the oracle."""
+    ours = _ours()
+    W, H = 3840, 2880                                    # 240 x 180 = 43 200 tiles -> 172.8 KB of histogram > 160 KB
+    scene = synth.make_scene(30_000, 91, sh_degree=1, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.01))
+    cam = synth.make_camera(W, H)
+    bg = torch.tensor([0.0, 0.0, 0.0])
+    args, out, fwd = ours.run_forward(scene, cam, bg)
+    o = gs_oracle.forward(scene.means3D, scene.opacity, scene.scales, scene.rotations, scene.sh, scene.degrees, bg=bg,
+                          viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, campos=cam.camera_center,
+                          W=W, H=H, tan_fovx=math.tan(cam.FoVx * 0.5), tan_fovy=math.tan(cam.FoVy * 0.5))
+    assert fwd["num_rendered"] == o["num_rendered"] > 0
+    for k in ("radii", "tiles_touched", "keys", "point_list", "ranges"):
+        assert np.array_equal(np.asarray(fwd[k]), np.asarray(o[k])), k
+    nb = ~o["borderline"]
+    assert np.array_equal(fwd["n_contrib"][nb], o["n_contrib"][nb])
+    assert np.abs(fwd["color"] - o["color"])[:, nb].max() <= 1e-4
+    dL = synth.grad_image(W, H, 92)
+    g = ours.run_backward(args, out, dL)
+    assert all(np.isfinite(v).all() for v in g.values())
