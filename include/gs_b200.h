@@ -120,16 +120,22 @@ typedef struct GsbGrads {
 	float* dL_dconic;       /* [P,4] optional export (reference keeps it internal, :262); may be NULL */
 	int32_t accumulate;     /* 0: outputs are overwritten (no caller memset needed). 1: per-view gradients are ADDED
 	                           to the buffers (view-batch accumulation for the sharded multi-GPU path) */
+	float* dL_dmeans2D_view;/* [P,3] optional, accumulate mode only: THIS view's screen-space gradient, overwritten — the
+	                           densification statistic is a per-view norm (scene/gaussian_model.py:693-695); may be NULL */
 } GsbGrads;
 
-/* Sizes of the three scratch blobs, for callers that pre-allocate. */
+/* Sizes of the three scratch blobs, for callers that pre-allocate.  gsb_image_bytes is the upper bound over all scenes of
+ * that image size; gsb_image_bytes_for is what gsb_forward requests for a scene of P Gaussians (quantised != 0: codebook ids). */
 GSB_API size_t gsb_geom_bytes(int32_t P);
 GSB_API size_t gsb_image_bytes(int32_t width, int32_t height);
+GSB_API size_t gsb_image_bytes_for(int32_t P, int32_t width, int32_t height, int32_t quantised);
 GSB_API size_t gsb_binning_bytes(int64_t num_rendered);
 
 /* Forward.  Writes out_color [3,H,W] and radii [P]; *num_rendered [host] receives R.
- * One stream synchronisation happens inside (the instance count sizes the binning blob, as in
- * rasterizer_impl.cu:445-450); everything else is asynchronous on `stream`. */
+ * The stream is never drained: the instance count (which sizes the binning blob, rasterizer_impl.cu:445-450) is copied to the
+ * host in the background while scatter / sort are already queued against the capacity recent frames needed, and the host
+ * waits for that copy's EVENT only.  binning_alloc may therefore be called with a size above gsb_binning_bytes(R), and a
+ * second time when R outgrew the speculation (the last blob handed out is the one to keep). */
 GSB_API int gsb_forward(const GsbScene* scene, const GsbCamera* cam,
                 gsb_alloc_fn geom_alloc, void* geom_user,
                 gsb_alloc_fn binning_alloc, void* binning_user,

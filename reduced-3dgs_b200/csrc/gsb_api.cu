@@ -6,15 +6,22 @@
 // Backward replaces Rasterizer::backward (rasterizer_impl.cu:508-630): render backward -> preprocess backward.
 // The entry points of the reduced-3dgs tools around the rasterizer (statistics forward, redundancy score, k-means, loss) are
 // thin argument checks in front of the launchers in gsb_tools.cu / gsb_kmeans.cu / gsb_loss.cu.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 #include "gsb_common.cuh"
 
 namespace gsb {
 
-unsigned long long g_launch_count = 0;
+// ---- process-wide state: all of it is either atomic, mutex-guarded or per thread; per-device facts are keyed by device ----
+static std::atomic<unsigned long long> g_launch_count{0};
+void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...)
@@ -24,31 +31,62 @@ void set_error(const char* fmt, ...)
 	va_end(ap);
 }
 
-// ---- per-kernel profiling --------------------------------------------------------------------
-static bool g_prof_on = false;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember the largest opt-in made for
+// each (kernel, device) pair instead of a process-wide "done" flag, so a second GPU driven from the same process gets its own.
+int ensure_dyn_smem(const void* kernel, int bytes)
+{
+	static std::mutex mu;
+	static std::map<std::pair<const void*, int>, int> done;
+	int dev = 0;
+	GSB_CUDA_OK(cudaGetDevice(&dev));
+	std::lock_guard<std::mutex> lk(mu);
+	int& have = done[std::make_pair(kernel, dev)];
+	if (have >= bytes) return GSB_OK;
+	GSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	have = bytes;
+	return GSB_OK;
+}
+
+int bin_plan_per_sm_override()
+{
+	static const int v = [] { const char* e = getenv("GSB_BIN_PER_SM"); const int x = e ? atoi(e) : 0; return x >= 1 && x <= 4 ? x : 0; }();
+	return v;
+}
+
+// ---- per-kernel profiling (events are created on the device that is current when they are first needed; the bench drives
+// one device per process).  The record list and the event pool are shared by all host threads: mutex-guarded; the "open"
+// event of a ProfScope belongs to the thread that opened it.
+static std::atomic<bool> g_prof_on{false};
 struct ProfRec { int kid; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
-static cudaEvent_t g_prof_cur = nullptr;
+static thread_local cudaEvent_t t_prof_cur = nullptr;
 static cudaEvent_t prof_event()
 {
-	if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+	{
+		std::lock_guard<std::mutex> lk(g_prof_mu);
+		if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+	}
 	cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 void prof_begin(int kid, cudaStream_t stream)
 {
 	(void)kid;
-	if (!g_prof_on) return;
-	g_prof_cur = prof_event();
-	cudaEventRecord(g_prof_cur, stream);
+	if (!g_prof_on.load(std::memory_order_relaxed)) return;
+	t_prof_cur = prof_event();
+	cudaEventRecord(t_prof_cur, stream);
 }
 void prof_end(int kid, cudaStream_t stream)
 {
-	if (!g_prof_on || !g_prof_cur) return;
+	if (!g_prof_on.load(std::memory_order_relaxed) || !t_prof_cur) return;
 	cudaEvent_t b = prof_event();
 	cudaEventRecord(b, stream);
-	g_prof_recs.push_back({ kid, g_prof_cur, b });
-	g_prof_cur = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(g_prof_mu);
+		g_prof_recs.push_back({ kid, t_prof_cur, b });
+	}
+	t_prof_cur = nullptr;
 }
 static const char* kKernelNames[K_COUNT] = { "preprocess", "tile_scan", "scatter", "tile_sort_large", "unused4", "tile_sort", "unused6",
 	"render_forward", "render_backward", "preprocess_backward", "mark_visible", "tools", "kmeans" };
@@ -57,7 +95,8 @@ int launch_debug_dequant(const GsbQuant*, int, float*, float*, cudaStream_t);
 int launch_preprocess(const GsbScene*, const GsbCamera*, const GeomState&, const ImageState&, const BinPlan&, int32_t*, const GsbDebug*, cudaStream_t);
 int launch_mark_visible(int, const float*, const float*, uint8_t*, cudaStream_t);
 int launch_tile_scan(const ImageState&, const GeomState&, const BinPlan&, int, int, cudaStream_t);
-int launch_binning(const GeomState&, const BinningState&, const ImageState&, const BinPlan&, int, long long, int, int, uint32_t, uint32_t, cudaStream_t);
+int launch_scatter_sort(const GeomState&, const BinningState&, const ImageState&, const BinPlan&, int, long long, int, int, cudaStream_t);
+int launch_sort_large(const GeomState&, const BinningState&, const ImageState&, int, int, uint32_t, uint32_t, cudaStream_t);
 int launch_export_binning(const GeomState&, const BinningState&, const ImageState&, int, int, uint64_t*, uint32_t*, cudaStream_t);
 int launch_render_forward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, float*, int32_t*, float*, cudaStream_t);
 int launch_sh_stats_update(int, int, const int*, const float*, const float*, const float*, const int*, const int*, const float*, float*, float*,
@@ -69,7 +108,7 @@ int launch_l1_ssim_forward(const float*, const float*, int, int, int, float*, fl
 int launch_l1_ssim_backward(const float*, const float*, int, int, int, const float*, float, const float*, float, const float*, float*, cudaStream_t);
 size_t kmeans_workspace_bytes(long long, int);
 int launch_kmeans(const float*, long long, const float*, int, float, int, int*, float*, char*, cudaStream_t);
-int launch_render_backward(const ImageState&, const BinningState&, const GeomState&, int, int, const float*, const float*, float*, cudaStream_t);
+int launch_render_backward(const ImageState&, const BinningState&, const GeomState&, int, int, int, const float*, const float*, float*, cudaStream_t);
 int launch_preprocess_backward(const GsbScene*, const GsbCamera*, const GeomState&, const int32_t*, const float*, const GsbGrads*, float, cudaStream_t);
 
 // geometry blob = GeomState followed by the backward's gradient accumulator (12 floats per Gaussian)
@@ -108,35 +147,63 @@ using namespace gsb;
 extern "C" {
 
 size_t gsb_geom_bytes(int32_t P) { return geom_state_bytes(P) + size_t(P) * 48 + 512; }
-// the image blob is sized for the largest per-CTA histogram table the forward can ask for (592 CTAs)
+// upper bound for callers that pre-allocate without knowing the scene (the largest per-CTA histogram table: 592 rows) ...
 size_t gsb_image_bytes(int32_t W, int32_t H) { size_t b; ImageState::carve(nullptr, W, H, &b, 148 * 4); return b + 256; }
+// ... and what the forward actually requests: the histogram rows of THIS scene's plan (none at all beyond the shared-memory limit)
+size_t gsb_image_bytes_for(int32_t P, int32_t W, int32_t H, int32_t quantised)
+{
+	const BinPlan plan = make_bin_plan(P, W, H, quantised != 0);
+	size_t b; ImageState::carve(nullptr, W, H, &b, plan.priv ? plan.ctas : 0); return b + 256;
+}
 size_t gsb_binning_bytes(int64_t R) { size_t b; BinningState::carve(nullptr, R, &b); return b + 256; }
-uint64_t gsb_launch_count(void) { return g_launch_count; }
+uint64_t gsb_launch_count(void) { return g_launch_count.load(); }
 const char* gsb_last_error(void) { return g_err; }
 const char* gsb_version(void) { return "gs_b200 0.1 (sm_100a)"; }
 
 void gsb_profile_enable(int on)
 {
-	g_prof_on = on != 0;
+	g_prof_on.store(on != 0);
 	// cudaEventCreate costs tens of microseconds: create the pool up front so the timed region only records
-	if (g_prof_on) while (g_prof_pool.size() < 4096) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; g_prof_pool.push_back(e); }
+	std::lock_guard<std::mutex> lk(g_prof_mu);
+	if (on) while (g_prof_pool.size() < 4096) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; g_prof_pool.push_back(e); }
 }
 
 int gsb_profile_read(int max_entries, const char** names, double* total_ms, uint64_t* launches)
 {
 	double ms[K_COUNT] = { 0 }; uint64_t n[K_COUNT] = { 0 };
-	for (auto& r : g_prof_recs)
+	std::vector<ProfRec> recs;
+	{
+		std::lock_guard<std::mutex> lk(g_prof_mu);
+		recs.swap(g_prof_recs);
+	}
+	for (auto& r : recs)
 	{
 		cudaEventSynchronize(r.b);
 		float t = 0.f;
 		if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kid] += t; n[r.kid]++; }
+		std::lock_guard<std::mutex> lk(g_prof_mu);
 		g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
 	}
-	g_prof_recs.clear();
 	int k = 0;
 	for (int i = 0; i < K_COUNT && k < max_entries; i++)
 		if (n[i]) { names[k] = kKernelNames[i]; total_ms[k] = ms[i]; launches[k] = n[i]; k++; }
 	return k;
+}
+
+// Host side of the instance-count read-back, per (host thread, device): a pinned landing buffer, the event that marks its
+// arrival, and the largest instance count seen recently (the capacity the next frame's binning blob is speculatively carved for).
+namespace {
+struct HostSide {
+	uint32_t* counters = nullptr;
+	cudaEvent_t arrived = nullptr;
+	long long r_hint = 0;
+	~HostSide()
+	{
+		if (counters) cudaFreeHost(counters);             // thread exit; errors (runtime already unloading) are irrelevant here
+		if (arrived) cudaEventDestroy(arrived);
+	}
+};
+static thread_local std::map<int, HostSide> t_host;
 }
 
 static int forward_impl(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_fn geom_alloc, void* geom_user,
@@ -156,29 +223,54 @@ static int forward_impl(const GsbScene* scene, const GsbCamera* cam, gsb_alloc_f
 		GSB_CUDA_OK(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), stream));
 		return GSB_OK;
 	}
+	const BinPlan plan = make_bin_plan(P, W, H, scene->quant != nullptr);
 	char* geom_blob = geom_alloc(geom_user, gsb_geom_bytes(P));
-	char* img_blob = image_alloc(image_user, gsb_image_bytes(W, H));
+	char* img_blob = image_alloc(image_user, gsb_image_bytes_for(P, W, H, scene->quant != nullptr));
 	if (!geom_blob || !img_blob) { set_error("scratch allocation failed"); return GSB_ENOMEM; }
 	GeomState g = GeomState::carve(geom_blob, P);
-	const BinPlan plan = make_bin_plan(P, W, H, scene->quant != nullptr);
 	ImageState img = ImageState::carve(img_blob, W, H, nullptr, plan.priv ? plan.ctas : 0);
 	GSB_CUDA_OK(cudaMemsetAsync(g.counters, 0, 16 * sizeof(uint32_t), stream));
 	if (!plan.priv) GSB_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, ImageState::tiles(W, H) * sizeof(uint32_t), stream));
 	if (int e = launch_preprocess(scene, cam, g, img, plan, radii, debug, stream)) return e;
 	if (int e = launch_tile_scan(img, g, plan, W, H, stream)) return e;
-	// the instance count sizes the binning blob (rasterizer_impl.cu:445-450): one 32-byte read-back (R, error flag, large-tile class sizes)
-	static thread_local uint32_t* h_counters = nullptr;
-	if (!h_counters) GSB_CUDA_OK(cudaMallocHost(&h_counters, 16 * sizeof(uint32_t)));
-	GSB_CUDA_OK(cudaMemcpyAsync(h_counters, g.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	GSB_CUDA_OK(cudaStreamSynchronize(stream));
-	const long long R = h_counters[0];
-	if (h_counters[3]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSB_ECUDA; }
-	if (R >= (1ll << 31)) { set_error("%lld (Gaussian, tile) instances do not fit 31 bits", R); return GSB_ERANGE; }
+
+	// The instance count R sizes the binning blob (rasterizer_impl.cu:445-450 reads it back and stalls the device meanwhile).
+	// Here it travels to the host in the background (32 bytes: R, error flags, large-tile class sizes) while the scatter and the
+	// per-tile sort are ALREADY queued behind it, carved for the capacity recent frames needed; the host then waits for the
+	// copy's event only — the stream keeps running — and re-launches in the rare case that R outgrew the speculation.
+	int dev = 0;
+	GSB_CUDA_OK(cudaGetDevice(&dev));
+	HostSide& hs = t_host[dev];
+	if (!hs.counters) GSB_CUDA_OK(cudaMallocHost(&hs.counters, 16 * sizeof(uint32_t)));
+	if (!hs.arrived) GSB_CUDA_OK(cudaEventCreateWithFlags(&hs.arrived, cudaEventDisableTiming));
+	GSB_CUDA_OK(cudaMemcpyAsync(hs.counters, g.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	GSB_CUDA_OK(cudaEventRecord(hs.arrived, stream));
+	long long cap = hs.r_hint > 0 ? hs.r_hint + hs.r_hint / 16 + 4096 : 0;
+	if (cap > 0x7fffffffll) cap = 0x7fffffffll;
+	BinningState b{};
+	if (cap > 0)
+	{
+		char* bin_blob = binning_alloc(binning_user, gsb_binning_bytes(cap));
+		if (!bin_blob) { set_error("binning allocation failed"); return GSB_ENOMEM; }
+		b = BinningState::carve(bin_blob, cap);
+		if (int e = launch_scatter_sort(g, b, img, plan, P, cap, W, H, stream)) return e;
+	}
+	GSB_CUDA_OK(cudaEventSynchronize(hs.arrived));
+	const uint32_t* hc = hs.counters;
+	if (hc[3]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSB_ECUDA; }
+	if (hc[6]) { set_error("the (Gaussian, tile) instance count does not fit 31 bits"); return GSB_ERANGE; }
+	const long long R = hc[0];
+	if (R > hs.r_hint || 2 * R < hs.r_hint) hs.r_hint = R;       // grows with the workload, restarts when a much smaller one begins
 	*num_rendered = R;
-	char* bin_blob = binning_alloc(binning_user, gsb_binning_bytes(R));
-	if (!bin_blob) { set_error("binning allocation failed"); return GSB_ENOMEM; }
-	BinningState b = BinningState::carve(bin_blob, R);
-	if (int e = launch_binning(g, b, img, plan, P, R, W, H, h_counters[4], h_counters[5], stream)) return e;
+	if (cap == 0 || R > cap)
+	{
+		// first frame of this thread on this device, or more instances than speculated (the guarded kernels above did nothing)
+		char* bin_blob = binning_alloc(binning_user, gsb_binning_bytes(R));
+		if (!bin_blob) { set_error("binning allocation failed"); return GSB_ENOMEM; }
+		b = BinningState::carve(bin_blob, R);
+		if (int e = launch_scatter_sort(g, b, img, plan, P, R, W, H, stream)) return e;
+	}
+	if (R > 0) if (int e = launch_sort_large(g, b, img, W, H, hc[4], hc[5], stream)) return e;
 	if (int e = launch_render_forward(img, b, g, W, H, cam->background, out_color, touched_pixels, transmittance, stream)) return e;
 	return GSB_OK;
 }
@@ -263,7 +355,7 @@ int gsb_kmeans(const float* values, int64_t n_values, const float* centers_in, i
 {
 	if (n_values < 0 || n_centers <= 0 || max_iterations < 0) { set_error("kmeans: bad sizes"); return GSB_EINVAL; }
 	if (!centers_in || !centers_out || (n_values > 0 && (!values || !ids || !workspace))) { set_error("kmeans: NULL argument"); return GSB_EINVAL; }
-	if (n_values >= (1ll << 31)) { set_error("kmeans: more than 2^31 values"); return GSB_ERANGE; }
+	if (n_values >= (1ll << 30)) { set_error("kmeans: 2^30 or more values (the look-back descriptors carry 30-bit counts)"); return GSB_ERANGE; }
 	return launch_kmeans(values, n_values, centers_in, n_centers, tol, max_iterations, ids, centers_out, workspace, (cudaStream_t)stream);
 }
 
@@ -293,8 +385,7 @@ int gsb_backward(const GsbScene* scene, const GsbCamera* cam, int64_t R, const i
 	ImageState img = ImageState::carve(const_cast<char*>(image_blob), W, H);
 	BinningState b = BinningState::carve(const_cast<char*>(binning_blob), R);
 	float* acc = reinterpret_cast<float*>(const_cast<char*>(geom_blob) + geom_state_bytes(P));
-	GSB_CUDA_OK(cudaMemsetAsync(acc, 0, size_t(P) * 48, stream));
-	if (int e = launch_render_backward(img, b, g, W, H, cam->background, dL_dout_color, acc, stream)) return e;
+	if (int e = launch_render_backward(img, b, g, P, W, H, cam->background, dL_dout_color, acc, stream)) return e;
 	if (int e = launch_preprocess_backward(scene, cam, g, radii, acc, grads, lambda_sh_sparsity, stream)) return e;
 	return GSB_OK;
 }

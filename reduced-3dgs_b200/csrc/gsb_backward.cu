@@ -14,14 +14,16 @@ struct BwdArgs {
 	int P, M, W, H;
 	float mod, tan_fovx, tan_fovy, focal_x, focal_y, lambda;
 	const float* means3D; const float* scales; const float* rotations; const float* cov3D_precomp;
-	const float* shs; const int32_t* degrees; const int32_t* radii;
+	const float* shs; const float* colors_precomp; const int32_t* degrees; const int32_t* radii;
 	const float* view; const float* proj; const float* campos;
 	int quant; GsbQuant q;
 	GeomState g; const float* acc;
 	GsbGrads out;
 };
 
-template <bool ACC> __device__ __forceinline__ void put(float* p, float v) { if (ACC) *p += v; else *p = v; }
+// ACC (view-batch accumulation): adding zero is a wasted read-modify-write — culled Gaussians and inactive SH bands are most
+// of the rows — so zeros are skipped; the overwrite mode stores them (every element written once, no memset by the caller).
+template <bool ACC> __device__ __forceinline__ void put(float* p, float v) { if (ACC) { if (v != 0.0f) *p += v; } else *p = v; }
 
 // Coalesced store of one small per-Gaussian output ([P,WD]) for the 32 Gaussians of a warp: lanes park their WD values in
 // shared memory, then the warp writes the 32*WD contiguous floats with unit-stride stores.
@@ -64,7 +66,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 	}
 	// rasterizer_impl.cu:549-571: sh_sparsity_multiplier = lambda / (n_visible * 15 * 3)
 	const float mult = a.lambda != 0.0f ? a.lambda / (float)((int)a.g.counters[1] * 15 * 3) : 0.0f;
-	const bool have_sh = (QUANT || a.shs != nullptr) && a.out.dL_dsh != nullptr;
+	// colours given by the caller (override_color): the SH coefficients were not used by the forward, their gradient is zero
+	const bool have_sh = (QUANT || a.shs != nullptr) && a.out.dL_dsh != nullptr && a.colors_precomp == nullptr;
 	const bool have_scales = QUANT || a.scales != nullptr;
 	for (long long base = ((long long)blockIdx.x * 8 + warp) * 32; base < a.P; base += (long long)gridDim.x * 8 * 32)
 	{
@@ -314,7 +317,11 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 				const int f = (i * 32 + lane) * 4, row = f / 48, col = f - row * 48;
 				const float* sp = s_row + row * RS + col;
 				float4 o = have_sh ? make_float4(sp[0], sp[1], sp[2], sp[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-				if (ACC) { const float4 c = dst4[i * 32 + lane]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+				if (ACC)
+				{
+					if (o.x == 0.f && o.y == 0.f && o.z == 0.f && o.w == 0.f) continue;      // nothing to add: no read-modify-write
+					const float4 c = dst4[i * 32 + lane]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+				}
 				dst4[i * 32 + lane] = o;
 			}
 		}
@@ -331,6 +338,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 			}
 		}
 		warp_store<3, ACC>(a.out.dL_dmeans2D, base, n_valid, o_m2, s_tmp, lane);
+		// accumulate mode: THIS view's screen-space gradient on its own (densification statistics are ||.|| per view, gaussian_model.py:693-695)
+		if (ACC && a.out.dL_dmeans2D_view) warp_store<3, false>(a.out.dL_dmeans2D_view, base, n_valid, o_m2, s_tmp, lane);
 		warp_store<3, ACC>(a.out.dL_dcolors, base, n_valid, o_col, s_tmp, lane);
 		warp_store<1, ACC>(a.out.dL_dopacity, base, n_valid, o_op, s_tmp, lane);
 		warp_store<3, ACC>(a.out.dL_dmeans3D, base, n_valid, o_m3, s_tmp, lane);
@@ -351,7 +360,7 @@ int launch_preprocess_backward(const GsbScene* s, const GsbCamera* cam, const Ge
 	a.focal_y = cam->height / (2.0f * cam->tan_fovy); a.focal_x = cam->width / (2.0f * cam->tan_fovx);   // rasterizer_impl.cu:573-574
 	a.lambda = lambda;
 	a.means3D = s->means3D; a.scales = s->scales; a.rotations = s->rotations; a.cov3D_precomp = s->cov3D_precomp;
-	a.shs = s->shs; a.degrees = s->degrees; a.radii = radii;
+	a.shs = s->shs; a.colors_precomp = s->colors_precomp; a.degrees = s->degrees; a.radii = radii;
 	a.view = cam->viewmatrix; a.proj = cam->projmatrix; a.campos = cam->campos;
 	a.quant = s->quant != nullptr; if (s->quant) a.q = *s->quant;
 	a.g = g; a.acc = acc; a.out = *grads;
@@ -361,8 +370,7 @@ int launch_preprocess_backward(const GsbScene* s, const GsbCamera* cam, const Ge
 	ProfScope prof(K_PREPROCESS_BWD, stream);
 #define GSB_LAUNCH_PB(Q, A)                                                                                          \
 	do {                                                                                                             \
-		static bool attr_set = false;                                                                                \
-		if (!attr_set) { GSB_CUDA_OK(cudaFuncSetAttribute(preprocess_backward_kernel<Q, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; } \
+		if (int e = ensure_dyn_smem((const void*)preprocess_backward_kernel<Q, A>, 160 * 1024)) return e;              \
 		preprocess_backward_kernel<Q, A><<<grid, 256, smem, stream>>>(a);                                            \
 	} while (0)
 	if (a.quant) { if (grads->accumulate) GSB_LAUNCH_PB(true, true); else GSB_LAUNCH_PB(true, false); }

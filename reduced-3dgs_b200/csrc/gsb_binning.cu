@@ -21,6 +21,7 @@
 // When the tile histogram does not fit in shared memory (> 160 KB, i.e. beyond ~8K images) counting and scattering fall
 // back to global atomics (tile_count / scatter_kernel).
 // (The first version of this file was a hand-written 8-bit onesweep radix sort; see git history and DESIGN.md.)
+#include <algorithm>
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 	uint32_t* __restrict__ counters, uint32_t* __restrict__ cursor, uint32_t* __restrict__ cls_list, uint32_t* __restrict__ cls_count)
 {
 	__shared__ uint32_t s_warp[32];
-	__shared__ uint32_t s_carry;
+	__shared__ unsigned long long s_carry;            // 64-bit: a total beyond 2^32 must not wrap silently
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0) { s_carry = 0; cls_count[0] = 0; cls_count[1] = 0; cls_count[2] = 0; }
 	__syncthreads();
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 			s_warp[lane] = w;
 		}
 		__syncthreads();
-		const uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
+		const unsigned long long start64 = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
+		const uint32_t start = (uint32_t)start64;       // positions are only used when the total fits 31 bits (checked below)
 		if (t < T)
 		{
 			ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);   // empty tiles stay (0,0) as after the reference's memset (RI:475)
@@ -61,12 +63,14 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 			if (c > GSB_SORT_CAP_A) { const int k = c > GSB_SORT_CAP_B; cls_list[k * T + atomicAdd(&cls_count[k], 1u)] = t; }
 		}
 		__syncthreads();
-		if (tid == 1023) s_carry = start + c;
+		if (tid == 1023) s_carry = start64 + c;
 		__syncthreads();
 	}
 	if (tid == 0)
 	{
-		counters[0] = s_carry;                      // num_rendered
+		const bool overflow = s_carry >= (1ull << 31);
+		counters[0] = overflow ? 0xffffffffu : (uint32_t)s_carry;   // num_rendered; the saturated value also stops every speculative launch
+		counters[6] = overflow ? 1u : 0u;
 		counters[4] = cls_count[0]; counters[5] = cls_count[1];   // read back with R: the host skips the large-tile launches when both are 0
 	}
 }
@@ -127,9 +131,13 @@ __device__ __forceinline__ void st_u64_policy(uint64_t* p, uint64_t v, uint64_t 
 
 // Scatter with privatised cursors: CTA c (same Gaussian chunk as in the preprocess kernel) starts every tile's cursor at
 // tile start + (instances of that tile owned by CTAs < c); slots are then claimed with shared-memory atomics only.
-__global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk, int T, const float4* __restrict__ rec, const uint2* __restrict__ rect,
-	const uint2* __restrict__ ranges, const uint32_t* __restrict__ cta_base, int gx, uint32_t y_lo, uint32_t y_hi, uint64_t* __restrict__ bucket)
+__global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk, int T, const uint32_t* __restrict__ depth_bits, const uint2* __restrict__ rect,
+	const uint2* __restrict__ ranges, const uint32_t* __restrict__ cta_base, int gx, uint32_t y_lo, uint32_t y_hi, uint64_t* __restrict__ bucket,
+	const uint32_t* __restrict__ counters, uint32_t cap)
 {
+	// The launch is speculative: the host sized `bucket` for `cap` instances before the instance count of THIS frame was known
+	// (it is still in flight to the host).  More instances than that: do nothing, the host re-launches with a larger blob.
+	if (counters[0] > cap) return;
 	// One launch handles the tile rows [y_lo, y_hi): when the bucket array is larger than L2 the host splits the image into row
 	// bands whose slice of the (tile-major) array fits, so that the scattered 8-byte stores still complete their sectors in L2.
 	extern __shared__ uint32_t s_cur[];
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk,
 		if (idx < last)
 		{
 			rc = __ldcs(&rect[idx]);
-			if (rc.x | rc.y) dbits = __float_as_uint(__ldcs(&rec[3 * (size_t)idx + 2]).z);
+			if (rc.x | rc.y) dbits = __ldcs(&depth_bits[idx]);
 		}
 		const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16;
 		const uint32_t miny = max(rc.y & 0xffffu, y_lo), maxy = min(rc.y >> 16, y_hi);       // clipped to this band
@@ -174,16 +182,18 @@ __global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk,
 
 // ------------------------------------------------------------------------------------------------
 // One thread per Gaussian writes its instances; Gaussians covering more than 32 tiles are handled by the whole warp.
-__global__ void __launch_bounds__(256) scatter_kernel(int P, const float4* __restrict__ rec, const uint2* __restrict__ rect,
-	const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, int gx, uint64_t* __restrict__ bucket)
+__global__ void __launch_bounds__(256) scatter_kernel(int P, const uint32_t* __restrict__ depth_bits, const uint2* __restrict__ rect,
+	const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, int gx, uint64_t* __restrict__ bucket,
+	const uint32_t* __restrict__ counters, uint32_t cap)
 {
+	if (counters[0] > cap) return;                   // speculative launch, see scatter_priv_kernel
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
 	uint2 rc = make_uint2(0, 0); uint32_t dbits = 0;
 	if (idx < P)
 	{
 		rc = rect[idx];
-		if (rc.x | rc.y) dbits = __float_as_uint(rec[3 * (size_t)idx + 2].z);
+		if (rc.x | rc.y) dbits = depth_bits[idx];
 	}
 	const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16, miny = rc.y & 0xffffu, maxy = rc.y >> 16;
 	const uint32_t w = maxx - minx, t = w * (maxy - miny);
@@ -220,8 +230,10 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, const float4* __res
 // Persistent CTAs walk a queued tile list (LIST is always true now; the one-CTA-per-tile mode is kept for tooling).
 template <int CAP, int THREADS, bool LIST>
 __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
-	uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cls_list, const uint32_t* __restrict__ cls_count)
+	uint32_t* __restrict__ point_list, const uint32_t* __restrict__ cls_list, const uint32_t* __restrict__ cls_count,
+	const uint32_t* __restrict__ counters, uint32_t cap)
 {
+	if (counters[0] > cap) return;                   // speculative launch, see scatter_priv_kernel
 	// LIST == false: cls_list is the per-tile flag array written by tile_sort_dist_kernel (only flagged tiles are sorted here)
 	constexpr int ITEMS = CAP / THREADS, NW = THREADS / 32;
 	extern __shared__ __align__(16) unsigned char s_raw[];
@@ -351,8 +363,10 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restr
 // (some bin > 32 keys) are flagged and handled by the radix kernel below, so the result never depends on the heuristic.
 #define DIST_BINS 2048
 __global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
-	uint32_t* __restrict__ point_list, uint32_t* __restrict__ fallback_list, uint32_t* __restrict__ fallback_count)
+	uint32_t* __restrict__ point_list, uint32_t* __restrict__ fallback_list, uint32_t* __restrict__ fallback_count,
+	const uint32_t* __restrict__ counters, uint32_t cap)
 {
+	if (counters[0] > cap) return;                   // speculative launch, see scatter_priv_kernel
 	__shared__ uint32_t s_bin[DIST_BINS];
 	__shared__ __align__(16) uint64_t s_out[GSB_SORT_CAP_A];
 	__shared__ uint32_t s_wtot[8];
@@ -516,57 +530,69 @@ int launch_tile_scan(const ImageState& img, const GeomState& g, const BinPlan& p
 	return GSB_OK;
 }
 
-int launch_binning(const GeomState& g, const BinningState& b, const ImageState& img, const BinPlan& plan, int P, long long R, int W, int H,
-	uint32_t n_tiles_over_a, uint32_t n_tiles_over_b, cudaStream_t stream)
+// Scatter + the per-tile sort classes that are launched unconditionally.  SPECULATIVE: `cap` is the instance capacity the
+// binning blob was carved for; every kernel here compares the device-side instance count with it and exits when it does not
+// fit (forward_impl then repeats the call with the true count).
+int launch_scatter_sort(const GeomState& g, const BinningState& b, const ImageState& img, const BinPlan& plan, int P, long long cap, int W, int H,
+	cudaStream_t stream)
 {
-	if (R == 0) return GSB_OK;
+	if (cap <= 0) return GSB_OK;
 	const int gx = (W + GSB_TILE_X - 1) / GSB_TILE_X, gy = (H + GSB_TILE_Y - 1) / GSB_TILE_Y;
 	const int T = gx * gy;
+	const uint32_t cap32 = (uint32_t)std::min<long long>(cap, 0x7fffffffll);
 	{
 		ProfScope prof(K_EMIT_KEYS, stream);
 		if (plan.priv)
 		{
-			static bool attr = false;
-			if (!attr) { GSB_CUDA_OK(cudaFuncSetAttribute(scatter_priv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024)); attr = true; }
+			if (int e = ensure_dyn_smem((const void*)scatter_priv_kernel, 180 * 1024)) return e;
 			// row bands: each band's slice of the bucket array (8 B x its instances, tile-major = contiguous) should fit L2
-			const int bands = (int)std::min<long long>(gy, std::max<long long>(1, (R * 8 + (104ll << 20) - 1) / (104ll << 20)));
+			const int bands = (int)std::min<long long>(gy, std::max<long long>(1, (cap * 8 + (104ll << 20) - 1) / (104ll << 20)));
 			const int rows = (gy + bands - 1) / bands;
 			for (int y0 = 0; y0 < gy; y0 += rows)
 			{
 				const int y1 = std::min(gy, y0 + rows);
-				scatter_priv_kernel<<<plan.ctas, plan.threads, size_t(y1 - y0) * gx * sizeof(uint32_t), stream>>>(P, plan.chunk, T, g.rec, g.rect,
-					img.ranges, img.cta_count, gx, (uint32_t)y0, (uint32_t)y1, b.bucket);
-				if (y0) GSB_LAUNCHED();
+				scatter_priv_kernel<<<plan.ctas, plan.threads, size_t(y1 - y0) * gx * sizeof(uint32_t), stream>>>(P, plan.chunk, T, g.dbits, g.rect,
+					img.ranges, img.cta_count, gx, (uint32_t)y0, (uint32_t)y1, b.bucket, g.counters, cap32);
+				GSB_LAUNCHED();
 			}
 		}
 		else
-			scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.rec, g.rect, img.ranges, img.tile_cursor, gx, b.bucket);
-		GSB_LAUNCHED();
+		{
+			scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.dbits, g.rect, img.ranges, img.tile_cursor, gx, b.bucket, g.counters, cap32);
+			GSB_LAUNCHED();
+		}
 	}
-	constexpr size_t smemA = size_t(GSB_SORT_CAP_A) * 16 + 8 * 256 * 4, smemB = size_t(GSB_SORT_CAP_B) * 16 + 32 * 256 * 4;
-	static bool attr_set = false;
-	if (!attr_set)
-	{
-		GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<GSB_SORT_CAP_A, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-		GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<GSB_SORT_CAP_B, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-		attr_set = true;
-	}
+	constexpr size_t smemA = size_t(GSB_SORT_CAP_A) * 16 + 8 * 256 * 4;
+	if (int e = ensure_dyn_smem((const void*)tile_sort_kernel<GSB_SORT_CAP_A, 256, true>, (int)smemA)) return e;
 	{
 		ProfScope prof(K_SORT_PASS, stream);
-		tile_sort_dist_kernel<<<T, 256, 0, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list + 2 * (size_t)T, img.cls_count + 2);
+		tile_sort_dist_kernel<<<T, 256, 0, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list + 2 * (size_t)T, img.cls_count + 2, g.counters, cap32);
 		GSB_LAUNCHED();
 	}
 	{
 		ProfScope prof(K_SORT_LARGE, stream);
 		// radix fallback for the tiles the distribution sort queued (device-side list; normally empty: the CTAs exit at once)
 		tile_sort_kernel<GSB_SORT_CAP_A, 256, true><<<148 * 4, 256, smemA, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list + 2 * (size_t)T,
-			img.cls_count + 2);
+			img.cls_count + 2, g.counters, cap32);
 		GSB_LAUNCHED();
 	}
-	if (n_tiles_over_a)                     // class sizes came back with R: nothing is launched for classes that are empty
+	GSB_CUDA_OK(cudaGetLastError());
+	return GSB_OK;
+}
+
+// The two large-tile classes (> GSB_SORT_CAP_A / > GSB_SORT_CAP_B instances): launched after the host has seen the class
+// sizes (they ride the instance-count read-back), nothing is launched for an empty class.
+int launch_sort_large(const GeomState& g, const BinningState& b, const ImageState& img, int W, int H, uint32_t n_tiles_over_a, uint32_t n_tiles_over_b,
+	cudaStream_t stream)
+{
+	const int T = ((W + GSB_TILE_X - 1) / GSB_TILE_X) * ((H + GSB_TILE_Y - 1) / GSB_TILE_Y);
+	constexpr size_t smemB = size_t(GSB_SORT_CAP_B) * 16 + 32 * 256 * 4;
+	if (n_tiles_over_a)
 	{
+		if (int e = ensure_dyn_smem((const void*)tile_sort_kernel<GSB_SORT_CAP_B, 1024, true>, (int)smemB)) return e;
 		ProfScope prof(K_SORT_LARGE, stream);
-		tile_sort_kernel<GSB_SORT_CAP_B, 1024, true><<<148, 1024, smemB, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list, img.cls_count);
+		tile_sort_kernel<GSB_SORT_CAP_B, 1024, true><<<148, 1024, smemB, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list, img.cls_count,
+			g.counters, 0xffffffffu);
 		GSB_LAUNCHED();
 	}
 	if (n_tiles_over_b)

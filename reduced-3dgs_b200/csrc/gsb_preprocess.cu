@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreArgs a)
 				rec[1] = make_float4(pix_x, pix_y, opacity, rgb[0]);
 				rec[2] = make_float4(rgb[1], rgb[2], tz, 0.0f);
 				a.g.clamped[idx] = (uint8_t)clamp_bits;
+				a.g.dbits[idx] = __float_as_uint(tz);
 				visible = true;
 				if (a.dbg.depths) a.dbg.depths[idx] = tz;
 				if (a.dbg.means2D) { a.dbg.means2D[2 * idx] = pix_x; a.dbg.means2D[2 * idx + 1] = pix_y; }
@@ -340,13 +341,7 @@ int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& 
 	a.prefiltered = cam->prefiltered;
 	const int blocks_needed = (s->P + 255) / 256;
 	const size_t smem = (a.quant ? GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE * sizeof(float) : 0) + (plan.priv ? plan.hist_bytes : 0);
-	static bool attr_set = false;
-	if (!attr_set)
-	{
-		GSB_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-		GSB_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-		attr_set = true;
-	}
+	if (int e = ensure_dyn_smem(a.quant ? (const void*)preprocess_kernel<true> : (const void*)preprocess_kernel<false>, 180 * 1024)) return e;
 	ProfScope prof(K_PREPROCESS, stream);
 	int grid = plan.priv ? plan.ctas : blocks_needed;
 	if (!plan.priv && a.quant && grid > 148 * 8) grid = 148 * 8;                         // persistent: amortise the table load

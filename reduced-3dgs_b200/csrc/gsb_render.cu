@@ -445,13 +445,14 @@ int launch_render_forward(const ImageState& img, const BinningState& b, const Ge
 	return GSB_OK;
 }
 
-int launch_render_backward(const ImageState& img, const BinningState& b, const GeomState& g, int W, int H, const float* bg,
+int launch_render_backward(const ImageState& img, const BinningState& b, const GeomState& g, int P, int W, int H, const float* bg,
 	const float* dL_dpix, float* acc, cudaStream_t stream)
 {
 	const dim3 grid((W + GSB_TILE_X - 1) / GSB_TILE_X, (H + GSB_TILE_Y - 1) / GSB_TILE_Y);
-	static bool attr_set = false;
-	if (!attr_set) { GSB_CUDA_OK(cudaFuncSetAttribute(render_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem))); attr_set = true; }
+	if (int e = ensure_dyn_smem((const void*)render_backward_kernel, (int)sizeof(BwdSmem))) return e;
 	ProfScope prof(K_RENDER_BWD, stream);
+	// the per-Gaussian accumulator the kernel reduces into (12 floats per Gaussian, inside the geometry blob)
+	GSB_CUDA_OK(cudaMemsetAsync(acc, 0, size_t(P) * 48, stream));
 	render_backward_kernel<<<grid, 256, sizeof(BwdSmem), stream>>>(img.ranges, b.point_list, W, H, g.rec, bg,
 		img.final_T, img.n_contrib, img.tile_max_contrib, dL_dpix, acc);
 	GSB_LAUNCHED();

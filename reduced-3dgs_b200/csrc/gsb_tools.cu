@@ -191,8 +191,7 @@ int launch_pixel_size(int P, const float* means3D, int n_cams, const float* w2nd
 	if (P <= 0) return GSB_OK;
 	if (n_cams > 1024) { set_error("find_minimum_projected_pixel_size: more than 1024 cameras per call"); return GSB_EINVAL; }
 	ProfScope prof(K_TOOLS, stream);
-	static bool attr = false;
-	if (!attr) { GSB_CUDA_OK(cudaFuncSetAttribute(pixel_size_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 32 * 4)); attr = true; }
+	if (int e = ensure_dyn_smem((const void*)pixel_size_kernel, 1024 * 32 * 4)) return e;
 	pixel_size_kernel<<<(P + 255) / 256, 256, (size_t)n_cams * 32 * sizeof(float), stream>>>(P, means3D, n_cams, w2ndc, w2ndc_inv, heights, widths,
 		pixel_sizes);
 	GSB_LAUNCHED();

@@ -153,10 +153,11 @@ def rasterize_gaussians_variableSH_bands(background, means3D, colors, opacity, s
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                                  projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degrees, campos, geomBuffer, R,
                                  binningBuffer, imageBuffer, lambda_sh_sparsity, debug, *, prune_mask=None, quant=None,
-                                 accumulate_into=None, want_conic=False):
+                                 accumulate_into=None, want_conic=False, view_means2D=None):
     """rasterize_points.h:65-88 RasterizeGaussiansBackwardCUDA ->
     (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations).
-    `accumulate_into`: the same 8-tuple from a previous call; gradients are added in place (view-batch accumulation)."""
+    `accumulate_into`: the same 8-tuple from a previous call; gradients are added in place (view-batch accumulation);
+    `view_means2D` ([P,3], accumulate mode): receives THIS view's dL_dmeans2D on its own (per-view densification statistics)."""
     device = _device_of(means3D)
     L = _lib.lib()
     keep = []
@@ -173,8 +174,11 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         else:
             outs = _carve_f32(device, [(P, 3), (P, 3), (P, 1), (P, 3), (P, 6), (P, M, 3), (P, 3), (P, 4)])
         conic = torch.empty((P, 4), dtype=torch.float32, device=device) if want_conic else None
+        if view_means2D is not None and (accumulate_into is None or tuple(view_means2D.shape) != (P, 3) or
+                                         view_means2D.dtype != torch.float32 or not view_means2D.is_contiguous()):
+            raise RuntimeError("view_means2D needs accumulate_into and a contiguous fp32 [P,3] tensor")
         g = GsbGrads(ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), ptr(outs[4]), ptr(outs[5]), ptr(outs[6]), ptr(outs[7]),
-                     ptr(conic), 1 if accumulate_into is not None else 0)
+                     ptr(conic), 1 if accumulate_into is not None else 0, ptr(view_means2D))
         radii = radii.to(device=device, dtype=torch.int32).contiguous()
         st = L.gsb_backward(C.byref(scene), C.byref(cam), int(R), ptr(radii), ptr(geomBuffer), ptr(binningBuffer),
                             ptr(imageBuffer), ptr(dL), C.byref(g), float(lambda_sh_sparsity), _lib.current_stream(device))

@@ -95,6 +95,14 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
                     shs = torch.cat([tensor.flatten() for tensor in shs])
         else:
             colors_precomp = override_color
+    else:
+        # quantised model: attributes are codebook ids, de-quantised inside the kernels.  override_color (depth / debug renders of
+        # the reference's callers) replaces the SH colours there too; the PyTorch-side SH / covariance paths have nothing to work on.
+        if pipe.convert_SHs_python or pipe.compute_cov3D_python:
+            raise RuntimeError("gaussian_renderer.render: pipe.convert_SHs_python / compute_cov3D_python need fp32 attributes; "
+                               "de-quantise the model first (QuantScene.dequantise()) or leave both options off")
+        if override_color is not None:
+            colors_precomp = override_color
 
     fps = 0
     if measure_fps:

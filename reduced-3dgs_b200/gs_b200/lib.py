@@ -45,7 +45,7 @@ class GsbGrads(C.Structure):
     _fields_ = [("dL_dmeans2D", C.c_void_p), ("dL_dcolors", C.c_void_p), ("dL_dopacity", C.c_void_p),
                 ("dL_dmeans3D", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p),
                 ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p), ("dL_dconic", C.c_void_p),
-                ("accumulate", C.c_int32)]
+                ("accumulate", C.c_int32), ("dL_dmeans2D_view", C.c_void_p)]
 
 
 _lib = None
@@ -80,6 +80,8 @@ def lib():
         L.gsb_geom_bytes.argtypes = [C.c_int32]
         L.gsb_image_bytes.restype = C.c_size_t
         L.gsb_image_bytes.argtypes = [C.c_int32, C.c_int32]
+        L.gsb_image_bytes_for.restype = C.c_size_t
+        L.gsb_image_bytes_for.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.gsb_binning_bytes.restype = C.c_size_t
         L.gsb_binning_bytes.argtypes = [C.c_int64]
         L.gsb_launch_count.restype = C.c_uint64
@@ -149,7 +151,7 @@ def profile_read() -> dict:
     return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(k)}
 
 
-EXPORTED_SYMBOLS = ["gsb_geom_bytes", "gsb_image_bytes", "gsb_binning_bytes", "gsb_forward", "gsb_backward",
+EXPORTED_SYMBOLS = ["gsb_geom_bytes", "gsb_image_bytes", "gsb_image_bytes_for", "gsb_binning_bytes", "gsb_forward", "gsb_backward",
                     "gsb_mark_visible", "gsb_export_binning", "gsb_export_image", "gsb_launch_count", "gsb_last_error",
                     "gsb_version", "gsb_profile_enable", "gsb_profile_read", "gsb_debug_dequant", "gsb_forward_statistics",
                     "gsb_sh_statistics_update", "gsb_min_projected_pixel_size", "gsb_sphere_ellipsoid_intersection",

@@ -20,8 +20,19 @@ from . import ply, synth
 
 class GaussianModelView:
     def __init__(self, scene: synth.Scene, device, quant: Optional[synth.QuantScene] = None, prune_mask: Optional[torch.Tensor] = None,
-                 requires_grad: bool = True):
+                 requires_grad: bool = True, variable_sh_bands: bool = False):
+        """`variable_sh_bands` (inference, reference GaussianModel(sh_degree, variable_sh_bands=True)): `get_features` is then the
+        reference's LIST of per-degree tensors [N_d, (d+1)^2, 3] (scene/gaussian_model.py:153-163) that
+        `render(..., variable_sh_bands=True)` flattens into the packed layout of rasterize_gaussians_variableSH_bands; the
+        Gaussians must be ordered by degree, as the reference's per-degree PLY groups are."""
         g = requires_grad
+        self.variable_sh_bands = variable_sh_bands
+        if variable_sh_bands:
+            deg = scene.degrees.view(-1)
+            if not bool((deg[1:] >= deg[:-1]).all()):
+                raise ValueError("variable_sh_bands needs Gaussians ordered by SH degree (the reduced-3dgs PLY groups)")
+            if quant is not None:
+                raise ValueError("variable_sh_bands is the fp32 packed-SH inference layout; a quantised model uses the fused id planes")
         self._xyz = scene.means3D.to(device).requires_grad_(g)
         self._opacity = scene.opacity.to(device).requires_grad_(g and quant is None)          # raw logits (GM:149-150 activates later)
         self._scaling = scene.scales.to(device).requires_grad_(g and quant is None)           # already exp-activated
@@ -36,7 +47,16 @@ class GaussianModelView:
     get_xyz = property(lambda s: s._xyz)
     get_scaling = property(lambda s: s._scaling)
     get_rotation = property(lambda s: s._rotation)
-    get_features = property(lambda s: s._features)
+    @property
+    def get_features(self):
+        if not self.variable_sh_bands:
+            return self._features
+        out, start = [], 0                                   # gaussian_model.py:153-163: cat(features_dc[group], features_rest[group]) per degree
+        for d, n in enumerate(self.per_band_count):
+            out.append(self._features[start:start + n, :(d + 1) ** 2, :])
+            start += n
+        return out
+
     num_primitives = property(lambda s: int(s._xyz.shape[0]))
 
     def params(self):

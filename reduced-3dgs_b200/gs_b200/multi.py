@@ -48,48 +48,77 @@ def broadcast_scene(tensors: Sequence[torch.Tensor], src: int = 0) -> None:
 class GradAccumulator:
     """Per-Gaussian gradient buffers that live across the views of a batch.
 
-    `buffers()` returns the 8-tuple in the order of rasterize_gaussians_backward (pass it as `accumulate_into`);
-    `observe_view()` folds the per-view, non-linear densification statistics; `all_reduce()` sums the buffers
-    over ranks in one flat collective per dtype."""
+    `buffers()` returns the 8-tuple in the order of rasterize_gaussians_backward (pass it as `accumulate_into`, and
+    `view_means2D` as the keyword of the same name); `observe_view()` folds the per-view, non-linear densification
+    statistics from THIS view's screen-space gradient; `all_reduce()` closes the batch with TWO collectives:
+
+      * one SUM over the flat payload: the 62 floats per Gaussian the optimiser consumes (dL_dmeans2D 3,
+        dL_dopacity 1, dL_dmeans3D 3, dL_dsh 3M, dL_dscales 3, dL_drotations 4 -> 14 + 3M, 62 at M = 16) followed by the two
+        additive statistics (xyz_gradient_accum, denom) — dL_dcolors / dL_dcov3D are intermediates nobody trains on when
+        SH and scale/rotation are the parameters, so they stay local (`local`, 9 floats per Gaussian, not communicated);
+      * one MAX over max_radii2D.
+    `all_reduce(async_op=True)` returns after launching both on the communication stream (NCCL) — `wait()` joins them —
+    so a caller can overlap the reduction with work that does not touch the buffers (the next batch's forward passes)."""
+
+    SENT = ("dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dscales", "dL_drotations")
 
     def __init__(self, P: int, M: int, device):
         self.P, self.M = P, M
-        widths = [3, 3, 1, 3, 6, 3 * M, 3, 4]
-        self.flat = torch.zeros(P * sum(widths), dtype=torch.float32, device=device)
-        self._views, off = [], 0
-        for name, w in zip(GRAD_NAMES, widths):
+        widths = dict(GRAD_WIDTH, dL_dsh=3 * M)
+        n_sent = sum(widths[n] for n in self.SENT)
+        self.floats_per_gaussian = n_sent                      # 62 at M = 16
+        self.flat = torch.zeros(P * (n_sent + 2), dtype=torch.float32, device=device)
+        self.local = torch.zeros(P * (widths["dL_dcolors"] + widths["dL_dcov3D"]), dtype=torch.float32, device=device)
+        views, off = {}, 0
+        for name in self.SENT:
+            w = widths[name]
             v = self.flat[off:off + P * w]
             off += P * w
-            self._views.append(v.view(P, M, 3) if name == "dL_dsh" else v.view(P, w))
-        # densification statistics (reference gaussian_model.py:693-695 add_densification_stats, train.py:134-139)
-        self.xyz_gradient_accum = torch.zeros(P, 1, dtype=torch.float32, device=device)
-        self.denom = torch.zeros(P, 1, dtype=torch.float32, device=device)
+            views[name] = v.view(P, M, 3) if name == "dL_dsh" else v.view(P, w)
+        # densification statistics (reference gaussian_model.py:693-695 add_densification_stats, train.py:134-139): additive ones
+        # ride at the end of the flat payload
+        self.xyz_gradient_accum = self.flat[off:off + P].view(P, 1)
+        self.denom = self.flat[off + P:off + 2 * P].view(P, 1)
+        views["dL_dcolors"] = self.local[:3 * P].view(P, 3)
+        views["dL_dcov3D"] = self.local[3 * P:].view(P, 6)
+        self._views = [views[n] for n in GRAD_NAMES]
         self.max_radii2D = torch.zeros(P, dtype=torch.float32, device=device)
+        self.view_means2D = torch.zeros(P, 3, dtype=torch.float32, device=device)   # written (not added to) by every backward
         self.n_views = 0
+        self._pending = []
 
     def buffers(self):
         return tuple(self._views)
 
     def zero_(self):
         self.flat.zero_()
+        self.local.zero_()
+        self.max_radii2D.zero_()
         self.n_views = 0
 
-    def observe_view(self, dL_dmeans2D_view: torch.Tensor, radii: torch.Tensor):
-        """Per-view statistics must be taken from THIS view's screen-space gradient, before it is summed with others."""
-        vis = radii > 0
-        self.xyz_gradient_accum[vis] += torch.norm(dL_dmeans2D_view[vis, :2], dim=-1, keepdim=True)
-        self.denom[vis] += 1
-        self.max_radii2D[vis] = torch.max(self.max_radii2D[vis], radii[vis].to(torch.float32))
+    def observe_view(self, radii: torch.Tensor, dL_dmeans2D_view: Optional[torch.Tensor] = None):
+        """Per-view statistics must be taken from THIS view's screen-space gradient (`view_means2D`, which the backward wrote
+        for the view just rendered), before it is summed with other views."""
+        g = self.view_means2D if dL_dmeans2D_view is None else dL_dmeans2D_view
+        vis = (radii > 0).view(-1, 1)
+        self.xyz_gradient_accum += torch.where(vis, torch.norm(g[:, :2], dim=-1, keepdim=True), torch.zeros_like(self.xyz_gradient_accum))
+        self.denom += vis.to(torch.float32)
+        self.max_radii2D = torch.where(vis.view(-1), torch.max(self.max_radii2D, radii.to(torch.float32)), self.max_radii2D)
         self.n_views += 1
 
-    def all_reduce(self):
+    def all_reduce(self, async_op: bool = False):
         _, w = world()
         if w == 1:
             return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        dist.all_reduce(self.xyz_gradient_accum, op=dist.ReduceOp.SUM)
-        dist.all_reduce(self.denom, op=dist.ReduceOp.SUM)
-        dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX)
+        self._pending = [dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True),
+                         dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, async_op=True)]
+        if not async_op:
+            self.wait()
+
+    def wait(self):
+        for h in self._pending:
+            h.wait()
+        self._pending = []
 
 
 def gather_images(image: torch.Tensor, dst: int = 0) -> Optional[List[torch.Tensor]]:

@@ -26,8 +26,12 @@ def test_host_only_entry_points():
     L = lib.lib()
     assert b"sm_100a" in L.gsb_version()
     g1, g2 = L.gsb_geom_bytes(1000), L.gsb_geom_bytes(2000)
-    assert 0 < g1 < g2 and g2 - g1 >= 1000 * 104          # rec 48 + rect 8 + clamped 1 + accumulator 48, modulo alignment
+    assert 0 < g1 < g2 and g2 - g1 >= 1000 * 104          # rec 48 + rect 8 + clamped 1 + depth bits 4 + accumulator 48, modulo alignment
     assert L.gsb_image_bytes(1920, 1080) >= 1920 * 1080 * 8
+    # what the forward requests follows the scene's histogram plan: never above the scene-independent bound, and no table at all
+    # once the tile histogram exceeds shared memory (8K image: global-atomics binning)
+    assert 1920 * 1080 * 8 <= L.gsb_image_bytes_for(3_000_000, 1920, 1080, 1) <= L.gsb_image_bytes(1920, 1080)
+    assert L.gsb_image_bytes_for(1000, 7680, 4320, 0) < 7680 * 4320 * 8 + 40 * (480 * 270) + 4096
     assert L.gsb_binning_bytes(10 ** 6) >= 10 ** 6 * 20
     assert L.gsb_launch_count() >= 0
 
@@ -36,7 +40,7 @@ def test_struct_layouts_match_header():
     # field order / sizes of the ctypes mirrors against the C declarations (x86-64 SysV)
     assert ctypes.sizeof(lib.GsbQuant) == 6 * 8
     assert ctypes.sizeof(lib.GsbCamera) == 4 * 4 + 4 * 8 + 8
-    assert ctypes.sizeof(lib.GsbGrads) == 9 * 8 + 8
+    assert ctypes.sizeof(lib.GsbGrads) == 9 * 8 + 8 + 8 and lib.GsbGrads.dL_dmeans2D_view.offset == 9 * 8 + 8
     assert ctypes.sizeof(lib.GsbDebug) == 7 * 8
     assert lib.GsbScene.means3D.offset == 8 and lib.GsbScene.scale_modifier.offset == 8 + 8 * 8
     assert lib.GsbScene.band_count.offset == lib.GsbScene.scale_modifier.offset + 8

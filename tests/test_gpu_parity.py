@@ -234,6 +234,32 @@ def test_prune_mask_equals_compacted_scene():
         assert np.abs(x - y).max() / (np.abs(y).max() + 1e-30) < 1e-4, n
 
 
+def test_prune_mask_against_oracle():
+    """Fused mask vs the CPU oracle's reference-equivalent computation (`gs_oracle.forward(prune_mask=)`: the reference run on the
+    physically compacted scene, outputs scattered back to the original indices — SURVEY §8(b), gaussian_model.py:553-563)."""
+    ours = _ours()
+    W, H = 320, 200
+    scene = synth.make_scene(20_000, 33, sh_degree=2, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.03))
+    cam = synth.make_camera(W, H)
+    bg = torch.tensor([0.2, 0.1, 0.05])
+    mask = synth.prune_mask(scene.P, 5)
+    o = gs_oracle.forward(scene.means3D, scene.opacity, scene.scales, scene.rotations, scene.sh, scene.degrees, bg=bg.numpy(),
+                          prune_mask=mask.numpy(), **cam_kw(cam, W, H))
+    _, _, fwd = ours.run_forward(scene, cam, bg, prune_mask=mask)
+    assert int(o["num_rendered"]) == fwd["num_rendered"]
+    for k in ("radii", "tiles_touched", "keys", "point_list", "ranges"):
+        assert np.array_equal(np.asarray(o[k]).reshape(-1), fwd[k].reshape(-1)), k
+    assert not fwd["radii"][mask.numpy().astype(bool)].any()
+    vis = o["radii"] > 0
+    assert np.array_equal(o["depths"][vis].view(np.uint32), fwd["depths"][vis].view(np.uint32))
+    for k in ("means2D", "cov3D", "rgb"):
+        assert np.array_equal(np.asarray(o[k])[vis], fwd[k][vis]), k
+    assert np.array_equal(o["conic_opacity"][vis, :3], fwd["conic_opacity"][vis, :3])     # opacity: oracle exp2f vs MUFU.EX2, <= 2 ulp
+    nb = ~o["borderline"]
+    assert np.array_equal(o["n_contrib"][nb], fwd["n_contrib"][nb]) and (~nb).mean() < 5e-3
+    assert np.abs(o["color"] - fwd["color"])[:, nb].max() <= 1e-4
+
+
 def test_fused_dequant_equals_dequantised_fp32():
     """Codebook ids + centres in the kernel == centers[ids] -> exp / normalize in PyTorch -> fp32 path."""
     ours = _ours()
@@ -307,6 +333,61 @@ def test_autograd_and_render_api():
     # determinism of the forward
     _, _, fwd2 = O.run_forward(scene, cam, bg)
     assert np.array_equal(fwd2["color"], fwd["color"]) and np.array_equal(fwd2["point_list"], fwd["point_list"])
+
+
+def test_render_variable_sh_bands_against_golden():
+    """gaussian_renderer.render(..., variable_sh_bands=True) (GR:84-86, 99-125) with the model's list-of-tensors get_features
+    (gaussian_model.py:153-163) == the reference's rasterize_gaussians_variableSH_bands output (golden g3, packed_*)."""
+    from types import SimpleNamespace
+    from gaussian_renderer import render
+    from gs_b200.model import GaussianModelView
+    ref = dict(np.load(os.path.join(GOLD, "g3.npz")))
+    c, scene, cam, bg, dL, extra = cases.build_inputs("g3")
+    pc = GaussianModelView(scene, "cuda", requires_grad=False, variable_sh_bands=True)
+    feats = pc.get_features
+    assert isinstance(feats, list) and [tuple(f.shape[1:]) for f in feats] == [(1, 3), (4, 3), (9, 3), (16, 3)]
+    assert [f.shape[0] for f in feats] == pc.per_band_count
+    pipe = SimpleNamespace(debug=False, convert_SHs_python=False, compute_cov3D_python=False)
+    with torch.no_grad():
+        pkg = render(cam.to("cuda"), pc, pipe, bg.cuda(), variable_sh_bands=True)
+    assert np.array_equal(pkg["radii"].cpu().numpy(), ref["packed_radii"])
+    assert np.array_equal(pkg["render"].cpu().numpy(), ref["packed_color"])
+    # and the dense path on the same model gives the same picture
+    pc2 = GaussianModelView(scene, "cuda", requires_grad=False)
+    with torch.no_grad():
+        img2 = render(cam.to("cuda"), pc2, pipe, bg.cuda())["render"]
+    assert np.array_equal(img2.cpu().numpy(), ref["packed_color"])
+
+
+def test_quantised_model_with_override_color():
+    """A quantised model rendered with override_color (reference callers: depth / debug renders) uses the given colours, forward
+    and backward, exactly like the fp32 path with colors_precomp; the python-side SH / covariance options are refused."""
+    from types import SimpleNamespace
+    from gaussian_renderer import render
+    from gs_b200.model import GaussianModelView
+    ours = _ours()
+    W, H = 320, 200
+    scene = synth.make_scene(20_000, 61, mixed_degrees=True, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.03))
+    q = synth.quantise_scene(scene)
+    deq = q.to("cuda").dequantise()
+    deq_cpu = synth.Scene(*[getattr(deq, f).cpu() for f in ("means3D", "opacity", "scales", "rotations", "sh", "degrees")])
+    cam = synth.make_camera(W, H).to("cuda")
+    bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    dL = synth.grad_image(W, H, 62).cuda()
+    col = torch.rand(scene.P, 3, generator=torch.Generator().manual_seed(63)).cuda().requires_grad_(True)
+    pipe = SimpleNamespace(debug=False, convert_SHs_python=False, compute_cov3D_python=False)
+    pc = GaussianModelView(deq_cpu, "cuda", quant=q)
+    pkg = render(cam, pc, pipe, bg, override_color=col)
+    (pkg["render"] * dL).sum().backward()
+    args, out, fwd = ours.run_forward(deq_cpu, cam, bg, extra={"colors_precomp": col.detach().cpu()})
+    g = ours.run_backward(args, out, dL)
+    assert np.abs(pkg["render"].detach().cpu().numpy() - fwd["color"]).max() <= 1e-6
+    assert np.array_equal(pkg["radii"].cpu().numpy(), fwd["radii"])
+    ref = g["dL_dcolors"]
+    assert np.abs(col.grad.cpu().numpy() - ref).max() <= 1e-4 * (np.abs(ref).max() + 1e-12)
+    assert float(pc.quant.grads["sh"].abs().max()) == 0.0, "SH coefficients were not used: their gradient is zero"
+    with pytest.raises(RuntimeError):
+        render(cam, pc, SimpleNamespace(debug=False, convert_SHs_python=True, compute_cov3D_python=False), bg)
 
 
 def test_full_size_properties():
@@ -407,3 +488,33 @@ def test_global_atomics_binning_path_beyond_shared_memory():
     dL = synth.grad_image(W, H, 92)
     g = ours.run_backward(args, out, dL)
     assert all(np.isfinite(v).all() for v in g.values())
+
+
+def test_second_device_in_the_same_process():
+    """The library keeps no process-wide per-device state: after cuda:0 has run every kernel, cuda:1 in the SAME process must get its
+    own dynamic-shared-memory opt-ins (preprocess 52 KB with codebooks, render backward 55 KB, per-tile sort) and its own
+    instance-count landing buffer, and produce identical results.  Needs 2 visible GPUs (skipped otherwise)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs in one process")
+    ours = _ours()
+    W, H = 640, 368
+    scene0 = synth.make_scene(60_000, 71, mixed_degrees=True, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.012))
+    q = synth.quantise_scene(scene0)
+    deq = q.to("cuda:0").dequantise()
+    scene = synth.Scene(*[getattr(deq, f).cpu() for f in ("means3D", "opacity", "scales", "rotations", "sh", "degrees")])
+    cam = synth.make_camera(W, H)
+    bg = torch.tensor([0.3, 0.2, 0.1])
+    dL = synth.grad_image(W, H, 72)
+    res = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        with torch.cuda.device(dev):
+            args, out, fwd = ours.run_forward(scene, cam, bg, quant=q, dev=dev)
+            g = ours.run_backward(args, out, dL, quant=q)
+            torch.cuda.synchronize(dev)
+        res.append((fwd, g))
+    for fwd, g in res[1:]:
+        for k in ("radii", "keys", "point_list", "ranges", "n_contrib", "color"):
+            assert np.array_equal(fwd[k], res[0][0][k]), k
+        for n in make_golden.GRAD_NAMES:
+            a, b = res[0][1][n].astype(np.float64), g[n].astype(np.float64)
+            assert np.abs(a - b).max() <= 2e-4 * (np.abs(a).max() + 1e-30), n

@@ -31,16 +31,23 @@ def _worker(rank, world, port, out):
         acc = multi.GradAccumulator(P, M, "cpu")
         bufs = acc.buffers()
         assert [tuple(b.shape) for b in bufs] == [(P, 3), (P, 3), (P, 1), (P, 3), (P, 6), (P, M, 3), (P, 3), (P, 4)]
+        assert acc.floats_per_gaussian == 14 + 3 * M and acc.flat.numel() == P * (14 + 3 * M + 2)     # 62 floats at M = 16 + 2 statistics
         for v in views:
-            g2d = torch.full((P, 3), float(v + 1))
             radii = torch.tensor([v % 2, 1, 0, 2, 3 * (v + 1)])
             for b in bufs:
                 b += (v + 1)
-            acc.observe_view(g2d, radii)
-        acc.all_reduce()
+            acc.view_means2D.fill_(float(v + 1))            # what the backward writes for this view (GsbGrads.dL_dmeans2D_view)
+            acc.observe_view(radii)
+        if rank == 0:
+            acc.all_reduce()
+        else:                                               # the asynchronous form: launch, then join
+            acc.all_reduce(async_op=True)
+            acc.wait()
         tot = sum(v + 1 for v in range(7))
-        for b in acc.buffers():
-            assert torch.all(b == tot)
+        own = sum(v + 1 for v in views)
+        for name, b in zip(multi.GRAD_NAMES, acc.buffers()):
+            # dL_dcolors / dL_dcov3D are not part of the communicated payload: they keep this rank's own sum
+            assert torch.all(b == (own if name in ("dL_dcolors", "dL_dcov3D") else tot)), name
         assert float(acc.denom[1]) == 7 and float(acc.denom[2]) == 0
         exp_norm = sum(math_sqrt2(v + 1) for v in range(7))
         assert abs(float(acc.xyz_gradient_accum[1]) - exp_norm) < 1e-4
@@ -77,4 +84,4 @@ def test_single_process_defaults():
     assert multi.shard_views(5) == [0, 1, 2, 3, 4]
     acc = multi.GradAccumulator(3, 1, "cpu")
     acc.all_reduce()
-    assert acc.flat.numel() == 3 * (3 + 3 + 1 + 3 + 6 + 3 + 3 + 4)
+    assert acc.flat.numel() == 3 * (3 + 1 + 3 + 3 + 3 + 4 + 2) and acc.local.numel() == 3 * 9

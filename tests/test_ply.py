@@ -1,7 +1,9 @@
 """CPU: reduced-3dgs PLY <-> device layout (gs_b200/ply.py; reference scene/gaussian_model.py:239-311 save_ply, :398-483 load_ply).
-`plyfile` is absent in this image, so the checks are: the header the writer emits is the one plyfile would emit for the
-reference's dtype lists, round trips are lossless (or exactly half-rounded), and the loaded id planes de-quantise to what the
-reference's `_parse_vertex_group` arithmetic (restated below with the same torch ops) produces."""
+PINNED to the reference: tests/golden/ref_{quant,quant_half,fp32}.ply were written by the reference's own
+`GaussianModel.save_ply` and ref_ply_expected.npz holds what its own `load_ply` / `_parse_vertex_group` read back
+(tests/golden/make_golden_ply.py imports /root/reference/scene/gaussian_model.py; only the `plyfile` container writer, absent in
+this image, is a stand-in).  Our reader must reproduce those tensors and our writer those bytes.  Further checks: header layout,
+lossless (or exactly half-rounded) round trips, and the reference's de-quantisation restated with its own torch ops."""
 import os
 import sys
 
@@ -118,3 +120,42 @@ def test_model_view_from_ply(tmp_path):
     assert torch.equal(v.get_scaling, d.scales) and torch.equal(v.get_rotation, d.rotations)
     t = GaussianModelView(scene, "cpu")                       # trainable fp32 view
     assert all(p.requires_grad for p in t.params()) and t.quant is None
+
+
+GOLD = os.path.join(HERE, "golden")
+
+
+@pytest.mark.parametrize("tag,quantised,half", [("quant", True, False), ("quant_half", True, True), ("fp32", False, False)])
+def test_files_written_by_the_reference(tmp_path, tag, quantised, half):
+    """Bytes written by the reference's save_ply -> our loader == what the reference's load_ply produced from the same bytes;
+    and for the quantised layouts our writer reproduces the reference's file byte for byte."""
+    path = os.path.join(GOLD, f"ref_{tag}.ply")
+    exp = {k[len(tag) + 1:]: v for k, v in np.load(os.path.join(GOLD, "ref_ply_expected.npz")).items() if k.startswith(tag + "_")}
+    m = ply.load_reduced_ply(path, half_float=half, quantised=quantised)
+    P = exp["xyz"].shape[0]
+    deg = torch.from_numpy(exp["degrees"]).view(-1)
+    assert torch.equal(m.means3D, torch.from_numpy(exp["xyz"])) and torch.equal(m.degrees.view(-1), deg)
+    ncoef = (deg.view(-1, 1).long() + 1) ** 2 - 1
+    active = (torch.arange(15).view(1, 15) < ncoef).unsqueeze(-1).expand(-1, -1, 3)
+    if quantised:
+        assert isinstance(m, synth.QuantScene) and m.ids_rest.dtype == torch.uint8
+        d = m.dequantise()                                      # scales exp-activated, rotations normalised, inactive bands zeroed
+        # raw (pre-activation) values exactly as _parse_vertex_group de-quantises them (gaussian_model.py:371-387)
+        c = m.centers
+        assert torch.equal(c[17][m.ids_scaling.long()], torch.from_numpy(exp["scaling"]))
+        rot_raw = torch.cat((c[18][m.ids_rot[:, 0:1].long()], c[19][m.ids_rot[:, 1:].long()]), dim=1)
+        assert torch.equal(rot_raw, torch.from_numpy(exp["rotation"]))
+        # the reference pads the ids of coefficients beyond a group's degree with 0 (:352-356), i.e. its tensor holds centre 0 there;
+        # the kernels never read those coefficients and dequantise() zeroes them (GM:726 semantics)
+        assert int(m.ids_rest[~active].sum()) == 0
+    else:
+        d = m
+    assert torch.equal(d.sh[:, :1], torch.from_numpy(exp["features_dc"]))
+    assert torch.equal(d.sh[:, 1:][active], torch.from_numpy(exp["features_rest"])[active])
+    assert torch.equal(d.opacity, torch.from_numpy(exp["opacity"]).view(P, 1))
+    assert torch.equal(d.scales, torch.from_numpy(exp["get_scaling"]))
+    assert torch.equal(d.rotations, torch.from_numpy(exp["get_rotation"]))
+    if quantised:
+        out = str(tmp_path / "rewritten.ply")
+        ply.save_reduced_ply(out, m, half_float=half)
+        assert open(out, "rb").read() == open(path, "rb").read(), "our writer must reproduce the reference-written file byte for byte"
