@@ -544,7 +544,7 @@ int launch_scatter_sort(const GeomState& g, const BinningState& b, const ImageSt
 		ProfScope prof(K_EMIT_KEYS, stream);
 		if (plan.priv)
 		{
-			if (int e = ensure_dyn_smem((const void*)scatter_priv_kernel, 180 * 1024)) return e;
+			if (int e = ensure_dyn_smem((const void*)scatter_priv_kernel, 220 * 1024)) return e;
 			// row bands: each band's slice of the bucket array (8 B x its instances, tile-major = contiguous) should fit L2
 			const int bands = (int)std::min<long long>(gy, std::max<long long>(1, (cap * 8 + (104ll << 20) - 1) / (104ll << 20)));
 			const int rows = (gy + bands - 1) / bands;

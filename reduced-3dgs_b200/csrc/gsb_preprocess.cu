@@ -20,6 +20,8 @@ struct PreArgs {
 	int quant; GsbQuant q;
 	GeomState g; int32_t* radii; uint32_t* tile_count;
 	int hist_priv, chunk, T; uint32_t* cta_count;      // privatised tile counting (gsb_common.cuh BinPlan)
+	int sh_vec4;                                       // dense fp32 SH rows can be read as 12 float4 (M == 16, 16-byte aligned)
+	int rest_aligned;                                  // QUANT: ids_rest is 16-byte aligned (warp-cooperative staging allowed)
 	GsbDebug dbg; int prefiltered;
 };
 
@@ -84,10 +86,20 @@ __device__ __forceinline__ void sh_to_rgb(int deg, float x, float y, float z, SH
 }
 
 
+// Load-path notes (measured, ncu round 1: the kernel was bound by L1 wavefronts, not by HBM).  A warp-wide 1- or 4-byte load
+// whose lanes are 45 B (codebook ids) or 192 B (fp32 SH row) apart touches one 128-byte line per lane and costs up to 32
+// L1 wavefronts; 45 such loads per Gaussian for the ids, 48 for a degree-3 SH row.  Hence:
+//   * fp32 SH rows (M == 16) are read with 128-bit loads straight from the row (12 instead of 48 load instructions);
+//   * the u8 ids of the SH rest coefficients are copied by the whole warp with 16-byte unit-stride loads (1440 contiguous bytes
+//     per 32 Gaussians) into a per-warp shared-memory buffer and picked up from there;
+//   * the four rotation ids are one 32-bit load.
+#define IDS_REST_ROW 45
+static_assert(32 * IDS_REST_ROW == GSB_IDS_STAGE_BYTES_PER_WARP, "staging buffer size");
+
 template <bool QUANT>
 __global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreArgs a)
 {
-	extern __shared__ float s_cb[];   // QUANT: [20][256] centres; scaling row holds exp(centre)
+	extern __shared__ __align__(16) float s_cb[];   // QUANT: [20][256] centres; scaling row holds exp(centre)
 	if (QUANT)
 	{
 		for (int i = threadIdx.x; i < GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE; i += blockDim.x)
@@ -99,11 +111,14 @@ __global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreArgs a)
 		__syncthreads();
 	}
 	uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_cb + (QUANT ? GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE : 0));
+	// QUANT: per-warp staging buffer of the rest-coefficient ids behind the histogram (16-byte aligned: T * 4 rounded up)
+	uint8_t* s_rest = reinterpret_cast<uint8_t*>(s_hist + ((a.hist_priv ? a.T : 0) + 3) / 4 * 4) + (threadIdx.x >> 5) * (32 * IDS_REST_ROW);
 	if (a.hist_priv)
 	{
 		for (int t = threadIdx.x; t < a.T; t += blockDim.x) s_hist[t] = 0;
 		__syncthreads();
 	}
+	const int lane = threadIdx.x & 31;
 	unsigned block_vis = 0;
 	// privatised counting: CTA c owns the contiguous Gaussians [c*chunk, (c+1)*chunk) (the scatter kernel uses the same map)
 	const long long first = a.hist_priv ? (long long)blockIdx.x * a.chunk : (long long)blockIdx.x * blockDim.x;
@@ -113,15 +128,17 @@ __global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreArgs a)
 	{
 		const long long idx = base + threadIdx.x;
 		bool visible = false;
-		uint32_t my_tiles = 0; uint2 my_rect = make_uint2(0, 0);
+		uint32_t tiles = 0; int radius_i = 0;
+		uint2 rect = make_uint2(0, 0);
+		float px = 0.f, py = 0.f, pz = 0.f, tz = 0.f, conx = 0.f, cony = 0.f, conz = 0.f, opacity = 0.f, pix_x = 0.f, pix_y = 0.f;
+		float cov3D[6];
+		// ---- geometry: cull, project, covariance, radius, tile rectangle --------------------------------
 		if (idx < last)
 		{
-			uint32_t tiles = 0; int radius_i = 0;
-			uint2 rect = make_uint2(0, 0);
 			do {
 				if (a.prune && a.prune[idx]) break;                                   // pruned == culled
-				const float px = a.means3D[3 * idx], py = a.means3D[3 * idx + 1], pz = a.means3D[3 * idx + 2];
-				const float tz = xform_row(a.view, 2, px, py, pz);                    // auxiliary.h:139-159
+				px = a.means3D[3 * idx]; py = a.means3D[3 * idx + 1]; pz = a.means3D[3 * idx + 2];
+				tz = xform_row(a.view, 2, px, py, pz);                                // auxiliary.h:139-159
 				if (tz <= 0.2f)
 				{
 					if (a.prefiltered) atomicExch(&a.g.counters[3], 1u);
@@ -132,13 +149,13 @@ __global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreArgs a)
 				const float hw = xform_row(a.proj, 3, px, py, pz);
 				const float p_w = __frcp_rn(__fadd_rn(hw, 0.0000001f));
 				const float projx = __fmul_rn(hx, p_w), projy = __fmul_rn(hy, p_w);
-				float cov3D[6];
 				float opac_raw;
 				if (QUANT)
 				{
 					const uint8_t* is = a.q.ids_scaling + 3 * idx;
-					const uint8_t* ir = a.q.ids_rot + 4 * idx;
-					float r = s_cb[18 * 256 + ir[0]], x = s_cb[19 * 256 + ir[1]], y = s_cb[19 * 256 + ir[2]], z = s_cb[19 * 256 + ir[3]];
+					const uint32_t ir = reinterpret_cast<const uint32_t*>(a.q.ids_rot)[idx];      // 4 ids, one load
+					float r = s_cb[18 * 256 + (ir & 0xffu)], x = s_cb[19 * 256 + ((ir >> 8) & 0xffu)], y = s_cb[19 * 256 + ((ir >> 16) & 0xffu)],
+						z = s_cb[19 * 256 + (ir >> 24)];
 					normalize_quat(r, x, y, z);
 					compute_cov3D(s_cb[17 * 256 + is[0]], s_cb[17 * 256 + is[1]], s_cb[17 * 256 + is[2]], a.mod, r, x, y, z, cov3D);
 					opac_raw = s_cb[16 * 256 + a.q.ids_opacity[idx]];
@@ -157,92 +174,142 @@ __global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreArgs a)
 					}
 					opac_raw = a.opacities[idx];
 				}
-				const float opacity = sigmoid_ref(opac_raw);
+				opacity = sigmoid_ref(opac_raw);
 				const float tx = xform_row(a.view, 0, px, py, pz), ty = xform_row(a.view, 1, px, py, pz);
 				const float3 cov = compute_cov2D(tx, ty, tz, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, a.view);
 				const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));   // forward.cu:419
 				if (det == 0.0f) break;
 				const float det_inv = __frcp_rn(det);
-				const float conx = __fmul_rn(cov.z, det_inv), cony = __fmul_rn(-cov.y, det_inv), conz = __fmul_rn(cov.x, det_inv);
+				conx = __fmul_rn(cov.z, det_inv); cony = __fmul_rn(-cov.y, det_inv); conz = __fmul_rn(cov.x, det_inv);
 				const float mid = __fmul_rn(0.5f, __fadd_rn(cov.x, cov.z));
 				const float sq = __fsqrt_rn(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
 				const float lambda1 = __fadd_rn(mid, sq), lambda2 = __fsub_rn(mid, sq);
 				const float my_radius = ceilf(__fmul_rn(3.0f, __fsqrt_rn(fmaxf(lambda1, lambda2))));
-				const float pix_x = ndc2pix(projx, a.W), pix_y = ndc2pix(projy, a.H);
+				pix_x = ndc2pix(projx, a.W); pix_y = ndc2pix(projy, a.H);
 				uint2 rmin, rmax;
 				get_rect(pix_x, pix_y, (int)my_radius, a.gx, a.gy, rmin, rmax);
 				if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) break;
-				// ---- colour -------------------------------------------------------------------------
-				float rgb[3]; unsigned clamp_bits = 0;
-				if (a.colors_precomp)
-				{
-#pragma unroll
-					for (int c = 0; c < 3; c++) rgb[c] = a.colors_precomp[3 * idx + c];
-				}
-				else
-				{
-					const float dx0 = __fsub_rn(px, a.campos[0]), dy0 = __fsub_rn(py, a.campos[1]), dz0 = __fsub_rn(pz, a.campos[2]);
-					float l2 = __fmul_rn(dy0, dy0);
-					l2 = __fmaf_rn(dx0, dx0, l2); l2 = __fmaf_rn(dz0, dz0, l2);
-					const float len = __fsqrt_rn(l2);
-					const float dx = __fdiv_rn(dx0, len), dy = __fdiv_rn(dy0, len), dz = __fdiv_rn(dz0, len);
-					float res[3];
-					if (QUANT)
-					{
-						const int deg = a.degrees[idx];
-						const uint8_t* idc = a.q.ids_dc + 3 * idx;
-						const uint8_t* irest = a.q.ids_rest + 45 * idx;
-						sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) {
-							return k == 0 ? s_cb[idc[c]] : s_cb[k * 256 + irest[3 * (k - 1) + c]]; }, res);
-					}
-					else if (a.packed)
-					{
-						// forward.cu:19-36 getSHOffset: degree follows from the position in the degree-sorted list
-						int deg = 0;
-						if (idx >= a.cum[0]) deg = 1;
-						if (idx >= a.cum[1]) deg = 2;
-						if (idx >= a.cum[2]) deg = 3;
-						const long long first = deg == 0 ? 0 : a.cum[deg - 1];
-						const float* sh = a.shs + 3 * (a.group_base[deg] + (idx - first) * (long long)((deg + 1) * (deg + 1)));
-						sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) { return sh[3 * k + c]; }, res);
-					}
-					else
-					{
-						const float* sh = a.shs + 3 * idx * a.M;
-						sh_to_rgb(a.degrees[idx], dx, dy, dz, [&](int k, int c) { return sh[3 * k + c]; }, res);
-					}
-#pragma unroll
-					for (int c = 0; c < 3; c++)
-					{
-						const float v = __fadd_rn(res[c], 0.5f);
-						clamp_bits |= (v < 0.0f) ? (1u << c) : 0u;
-						rgb[c] = fmaxf(v, 0.0f);
-					}
-				}
-				// ---- stores -------------------------------------------------------------------------
 				radius_i = (int)my_radius;
 				tiles = (rmax.y - rmin.y) * (rmax.x - rmin.x);
 				rect = make_uint2(rmin.x | (rmax.x << 16), rmin.y | (rmax.y << 16));
-				const float pth = -__logf(255.0f * opacity) - 1e-3f;
-				float4* rec = a.g.rec + 3 * idx;
-				rec[0] = make_float4(conx, cony, conz, pth);
-				rec[1] = make_float4(pix_x, pix_y, opacity, rgb[0]);
-				rec[2] = make_float4(rgb[1], rgb[2], tz, 0.0f);
-				a.g.clamped[idx] = (uint8_t)clamp_bits;
-				a.g.dbits[idx] = __float_as_uint(tz);
 				visible = true;
-				if (a.dbg.depths) a.dbg.depths[idx] = tz;
-				if (a.dbg.means2D) { a.dbg.means2D[2 * idx] = pix_x; a.dbg.means2D[2 * idx + 1] = pix_y; }
-				if (a.dbg.cov3D) { for (int k = 0; k < 6; k++) a.dbg.cov3D[6 * idx + k] = cov3D[k]; }
-				if (a.dbg.conic_opacity) reinterpret_cast<float4*>(a.dbg.conic_opacity)[idx] = make_float4(conx, cony, conz, opacity);
-				if (a.dbg.rgb) { for (int c = 0; c < 3; c++) a.dbg.rgb[3 * idx + c] = rgb[c]; }
-				if (a.dbg.clamped) { for (int c = 0; c < 3; c++) a.dbg.clamped[3 * idx + c] = (clamp_bits >> c) & 1u; }
 			} while (false);
+		}
+		// ---- colour -----------------------------------------------------------------------------------
+		const bool want_sh = visible && !a.colors_precomp;
+		int deg = 0;
+		if (want_sh)
+		{
+			if (!QUANT && a.packed)
+			{
+				// forward.cu:19-36 getSHOffset: degree follows from the position in the degree-sorted list
+				if (idx >= a.cum[0]) deg = 1;
+				if (idx >= a.cum[1]) deg = 2;
+				if (idx >= a.cum[2]) deg = 3;
+			}
+			else deg = a.degrees[idx];
+		}
+		bool staged = false;
+		if (QUANT)
+		{
+			// the warp's 32 rows of rest-coefficient ids are 1440 contiguous bytes: copy them with unit-stride 16-byte loads
+			// (full warps only — the array's last, partial warp reads its bytes directly; rest_aligned: the base pointer is 16-byte aligned)
+			const long long wbase = idx - lane;
+			if (__any_sync(0xffffffffu, want_sh && deg > 0) && a.rest_aligned && wbase + 32 <= (long long)a.P)
+			{
+				const uint4* src = reinterpret_cast<const uint4*>(a.q.ids_rest + wbase * IDS_REST_ROW);
+				uint4* dst = reinterpret_cast<uint4*>(s_rest);
+				__syncwarp();
+#pragma unroll
+				for (int c = lane; c < 32 * IDS_REST_ROW / 16; c += 32) dst[c] = __ldcs(src + c);
+				__syncwarp();
+				staged = true;
+			}
+		}
+		if (visible)
+		{
+			float rgb[3]; unsigned clamp_bits = 0;
+			if (a.colors_precomp)
+			{
+#pragma unroll
+				for (int c = 0; c < 3; c++) rgb[c] = a.colors_precomp[3 * idx + c];
+			}
+			else
+			{
+				const float dx0 = __fsub_rn(px, a.campos[0]), dy0 = __fsub_rn(py, a.campos[1]), dz0 = __fsub_rn(pz, a.campos[2]);
+				float l2 = __fmul_rn(dy0, dy0);
+				l2 = __fmaf_rn(dx0, dx0, l2); l2 = __fmaf_rn(dz0, dz0, l2);
+				const float len = __fsqrt_rn(l2);
+				const float dx = __fdiv_rn(dx0, len), dy = __fdiv_rn(dy0, len), dz = __fdiv_rn(dz0, len);
+				float res[3];
+				if (QUANT)
+				{
+					const uint8_t* idc = a.q.ids_dc + 3 * idx;
+					if (staged)
+					{
+						const uint8_t* irest = s_rest + lane * IDS_REST_ROW;
+						sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) {
+							return k == 0 ? s_cb[idc[c]] : s_cb[k * 256 + irest[3 * (k - 1) + c]]; }, res);
+					}
+					else
+					{
+						const uint8_t* irest = a.q.ids_rest + IDS_REST_ROW * idx;
+						sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) {
+							return k == 0 ? s_cb[idc[c]] : s_cb[k * 256 + irest[3 * (k - 1) + c]]; }, res);
+					}
+				}
+				else if (a.packed)
+				{
+					const long long gfirst = deg == 0 ? 0 : a.cum[deg - 1];
+					const float* sh = a.shs + 3 * (a.group_base[deg] + (idx - gfirst) * (long long)((deg + 1) * (deg + 1)));
+					sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) { return sh[3 * k + c]; }, res);
+				}
+				else if (a.sh_vec4)
+				{
+					// M == 16, 16-byte aligned tensor: the row is 12 float4; every coefficient below is a compile-time slot of one of
+					// them, repeated loads of the same float4 are merged by the compiler (read-only path), and only the float4 of the
+					// Gaussian's active bands are ever requested
+					const float4* row = reinterpret_cast<const float4*>(a.shs) + 12 * idx;
+					sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) {
+						const float4 q = __ldg(row + ((3 * k + c) >> 2));
+						const int e = (3 * k + c) & 3;
+						return e == 0 ? q.x : (e == 1 ? q.y : (e == 2 ? q.z : q.w)); }, res);
+				}
+				else
+				{
+					const float* sh = a.shs + 3 * idx * a.M;
+					sh_to_rgb(deg, dx, dy, dz, [&](int k, int c) { return sh[3 * k + c]; }, res);
+				}
+#pragma unroll
+				for (int c = 0; c < 3; c++)
+				{
+					const float v = __fadd_rn(res[c], 0.5f);
+					clamp_bits |= (v < 0.0f) ? (1u << c) : 0u;
+					rgb[c] = fmaxf(v, 0.0f);
+				}
+			}
+			// ---- stores -------------------------------------------------------------------------
+			const float pth = -__logf(255.0f * opacity) - 1e-3f;
+			float4* rec = a.g.rec + 3 * idx;
+			rec[0] = make_float4(conx, cony, conz, pth);
+			rec[1] = make_float4(pix_x, pix_y, opacity, rgb[0]);
+			rec[2] = make_float4(rgb[1], rgb[2], tz, 0.0f);
+			a.g.clamped[idx] = (uint8_t)clamp_bits;
+			a.g.dbits[idx] = __float_as_uint(tz);
+			if (a.dbg.depths) a.dbg.depths[idx] = tz;
+			if (a.dbg.means2D) { a.dbg.means2D[2 * idx] = pix_x; a.dbg.means2D[2 * idx + 1] = pix_y; }
+			if (a.dbg.cov3D) { for (int k = 0; k < 6; k++) a.dbg.cov3D[6 * idx + k] = cov3D[k]; }
+			if (a.dbg.conic_opacity) reinterpret_cast<float4*>(a.dbg.conic_opacity)[idx] = make_float4(conx, cony, conz, opacity);
+			if (a.dbg.rgb) { for (int c = 0; c < 3; c++) a.dbg.rgb[3 * idx + c] = rgb[c]; }
+			if (a.dbg.clamped) { for (int c = 0; c < 3; c++) a.dbg.clamped[3 * idx + c] = (clamp_bits >> c) & 1u; }
+		}
+		if (idx < last)
+		{
 			a.radii[idx] = radius_i;
 			a.g.rect[idx] = rect;
 			if (a.dbg.tiles_touched) a.dbg.tiles_touched[idx] = tiles;
-			my_tiles = tiles; my_rect = rect;
 		}
+		const uint32_t my_tiles = tiles; const uint2 my_rect = rect;
 		// per-tile instance counts (what the reference derives from sorted keys in identifyTileRanges): one RED per
 		// (Gaussian, tile); Gaussians covering more than 32 tiles are spread over the warp
 		{
@@ -339,13 +406,18 @@ int launch_preprocess(const GsbScene* s, const GsbCamera* cam, const GeomState& 
 	a.hist_priv = plan.priv; a.chunk = plan.chunk; a.T = a.gx * a.gy; a.cta_count = img.cta_count;
 	if (dbg) a.dbg = *dbg;
 	a.prefiltered = cam->prefiltered;
+	a.sh_vec4 = !a.quant && !a.packed && a.shs && a.M == 16 && (reinterpret_cast<uintptr_t>(a.shs) & 15) == 0;
+	a.rest_aligned = a.quant && (reinterpret_cast<uintptr_t>(a.q.ids_rest) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.q.ids_rot) & 3) == 0;
+	if (a.quant && (reinterpret_cast<uintptr_t>(a.q.ids_rot) & 3) != 0) { set_error("quantised scene: ids_rot must be 4-byte aligned"); return GSB_EINVAL; }
 	const int blocks_needed = (s->P + 255) / 256;
-	const size_t smem = (a.quant ? GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE * sizeof(float) : 0) + (plan.priv ? plan.hist_bytes : 0);
-	if (int e = ensure_dyn_smem(a.quant ? (const void*)preprocess_kernel<true> : (const void*)preprocess_kernel<false>, 180 * 1024)) return e;
+	const int threads = plan.priv ? plan.threads : 256;
+	const size_t hist_words = plan.priv ? (plan.hist_bytes / 4 + 3) / 4 * 4 : 0;
+	const size_t smem = (a.quant ? GSB_NUM_CODEBOOKS * GSB_CODEBOOK_SIZE * sizeof(float) : 0) + hist_words * 4 +
+		(a.quant ? size_t(threads / 32) * 32 * IDS_REST_ROW : 0);
+	if (int e = ensure_dyn_smem(a.quant ? (const void*)preprocess_kernel<true> : (const void*)preprocess_kernel<false>, 220 * 1024)) return e;
 	ProfScope prof(K_PREPROCESS, stream);
 	int grid = plan.priv ? plan.ctas : blocks_needed;
 	if (!plan.priv && a.quant && grid > 148 * 8) grid = 148 * 8;                         // persistent: amortise the table load
-	const int threads = plan.priv ? plan.threads : 256;
 	if (a.quant) preprocess_kernel<true><<<grid, threads, smem, stream>>>(a);
 	else preprocess_kernel<false><<<grid, threads, smem, stream>>>(a);
 	GSB_LAUNCHED();
