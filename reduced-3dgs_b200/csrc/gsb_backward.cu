@@ -21,9 +21,16 @@ struct BwdArgs {
 	GsbGrads out;
 };
 
-// ACC (view-batch accumulation): adding zero is a wasted read-modify-write — culled Gaussians and inactive SH bands are most
-// of the rows — so zeros are skipped; the overwrite mode stores them (every element written once, no memset by the caller).
-template <bool ACC> __device__ __forceinline__ void put(float* p, float v) { if (ACC) { if (v != 0.0f) *p += v; } else *p = v; }
+// ACC (view-batch accumulation): the sums are formed by the L2 with fire-and-forget reductions (RED.ADD, no value returns to
+// the SM): a load-add-store in the kernel serialises one DRAM round trip per output element behind the previous store
+// (measured: preprocess backward 0.30 -> 0.76 ms at 3 M Gaussians).  One kernel per view runs at a time on the stream, so every
+// element receives exactly one addition per view, in view order: the result is deterministic.  Adding zero is skipped — culled
+// Gaussians and inactive SH bands are most of the rows; the overwrite mode stores them (every element written once, no memset).
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d)
+{
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <bool ACC> __device__ __forceinline__ void put(float* p, float v) { if (ACC) { if (v != 0.0f) atomicAdd(p, v); } else *p = v; }
 
 // Coalesced store of one small per-Gaussian output ([P,WD]) for the 32 Gaussians of a warp: lanes park their WD values in
 // shared memory, then the warp writes the 32*WD contiguous floats with unit-stride stores.
@@ -319,10 +326,9 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 				float4 o = have_sh ? make_float4(sp[0], sp[1], sp[2], sp[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
 				if (ACC)
 				{
-					if (o.x == 0.f && o.y == 0.f && o.z == 0.f && o.w == 0.f) continue;      // nothing to add: no read-modify-write
-					const float4 c = dst4[i * 32 + lane]; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+					if (o.x != 0.f || o.y != 0.f || o.z != 0.f || o.w != 0.f) red_add_f32x4(reinterpret_cast<float*>(dst4 + i * 32 + lane), o.x, o.y, o.z, o.w);
 				}
-				dst4[i * 32 + lane] = o;
+				else dst4[i * 32 + lane] = o;
 			}
 		}
 		else if (a.out.dL_dsh)

@@ -14,7 +14,7 @@ import math
 import torch
 
 from gs_b200 import lib as _lib
-from gs_b200.lib import GsbCamera, GsbDebug, GsbGrads, GsbQuant, GsbScene, BlobAllocator, f32, ptr
+from gs_b200.lib import GsbCamera, GsbDebug, GsbGrads, GsbQuant, GsbScene, BlobAllocator, f32, on_device, ptr
 
 
 def _carve_f32(device, shapes):
@@ -33,7 +33,8 @@ def _carve_f32(device, shapes):
 def _device_of(means3D: torch.Tensor) -> torch.device:
     if not means3D.is_cuda:
         raise RuntimeError("gs_b200: means3D must live on a CUDA device (no CPU path exists)")
-    return means3D.device
+    d = means3D.device
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
 
 
 def _camera(device, bg, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, prefiltered, keep):
@@ -99,13 +100,14 @@ def _forward(background, means3D, colors, opacity, scales, rotations, scale_modi
     L = _lib.lib()
     keep = []
     H, W = int(image_height), int(image_width)
-    with torch.cuda.device(device):
+    with on_device(device):
         scene, P, M = _scene(device, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, sh, degrees,
                              keep, packed_counts, prune_mask, quant)
         cam = _camera(device, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, prefiltered, keep)
         out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
         radii = torch.empty((P,), dtype=torch.int32, device=device)
-        geom, binning, img = BlobAllocator(device, "geom"), BlobAllocator(device, "binning"), BlobAllocator(device, "image")
+        blobs = BlobAllocator.for_device(device)
+        cbs = blobs.cb
         dbg_ptr = None
         if debug_out is not None:
             d = dict(depths=torch.zeros(P, device=device), means2D=torch.zeros(P, 2, device=device),
@@ -117,16 +119,17 @@ def _forward(background, means3D, colors, opacity, scales, rotations, scale_modi
             dbg_ptr = C.pointer(dbg)
         R = C.c_int64(0)
         if statistics is not None:                               # (touched_pixels int32 [P,1], transmittance_sum f32 [P,1]) to fill
-            st = L.gsb_forward_statistics(C.byref(scene), C.byref(cam), geom.cb, None, binning.cb, None, img.cb, None,
+            st = L.gsb_forward_statistics(C.byref(scene), C.byref(cam), cbs["geom"], None, cbs["binning"], None, cbs["image"], None,
                                           out_color.data_ptr(), ptr(radii), C.byref(R), ptr(statistics[0]), ptr(statistics[1]),
                                           _lib.current_stream(device))
         else:
-            st = L.gsb_forward(C.byref(scene), C.byref(cam), geom.cb, None, binning.cb, None, img.cb, None,
+            st = L.gsb_forward(C.byref(scene), C.byref(cam), cbs["geom"], None, cbs["binning"], None, cbs["image"], None,
                                out_color.data_ptr(), ptr(radii), C.byref(R), dbg_ptr, _lib.current_stream(device))
+        geomB, binB, imgB = blobs.take("geom"), blobs.take("binning"), blobs.take("image")
         _lib.check(st)
         if debug:
             torch.cuda.synchronize(device)                      # reference CHECK_CUDA(debug) semantics, auxiliary.h:161-168
-    return int(R.value), out_color, radii, geom.tensor, binning.tensor, img.tensor
+    return int(R.value), out_color, radii, geomB, binB, imgB
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
@@ -162,7 +165,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     L = _lib.lib()
     keep = []
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
-    with torch.cuda.device(device):
+    with on_device(device):
         scene, P, M = _scene(device, means3D, colors, None, scales, rotations, scale_modifier, cov3D_precomp, sh, degrees, keep,
                              None, prune_mask, quant)
         if quant is None:
@@ -224,7 +227,7 @@ def calculate_colours_variance(cam_positions, means3D, opacity, scales, rotation
     for i in range(n_cams):
         _, _, radii, _, _, _ = _forward(bg, means3D, empty, opacity, scales, rotations, 1.0, empty, views[i], projs[i], txs[i], tys[i],
                                         Hs[i], Ws[i], sh, deg, cam_positions[i], False, False, statistics=(touched, tsum))
-        with torch.cuda.device(device):
+        with on_device(device):
             _lib.check(L.gsb_sh_statistics_update(P, M, ptr(deg), ptr(means3D), cam_positions[i].data_ptr(), ptr(sh), ptr(radii), ptr(touched),
                                                   ptr(tsum), ptr(wsum), ptr(wsumsq), ptr(dist), ptr(mean), ptr(var), stream))
     return dist / wsum, var / wsum.view(-1, 1, 1), mean
@@ -240,7 +243,7 @@ def find_minimum_projected_pixel_size(w2ndc_transforms, w2ndc_transforms_inverse
         return out
     i32 = lambda t: t.to(device=device, dtype=torch.int32).contiguous()
     m, mi, xyz, hs, ws = f32(w2ndc_transforms, device), f32(w2ndc_transforms_inverse, device), f32(means3D, device), i32(image_height), i32(image_width)
-    with torch.cuda.device(device):
+    with on_device(device):
         _lib.check(L.gsb_min_projected_pixel_size(P, ptr(xyz), n, ptr(m), ptr(mi), ptr(hs), ptr(ws), ptr(out), _lib.current_stream(device)))
     return out
 
@@ -256,7 +259,7 @@ def sphere_ellipsoid_intersection(means3D, scales, rotations, neighbours_indices
         return red, mask
     nb = neighbours_indices.to(device=device, dtype=torch.int32).contiguous()
     xyz, sc, rot, rad = f32(means3D, device), f32(scales, device), f32(rotations, device), f32(sphere_radius, device)
-    with torch.cuda.device(device):
+    with on_device(device):
         _lib.check(L.gsb_sphere_ellipsoid_intersection(P, ptr(xyz), ptr(sc), ptr(rot), ptr(nb), ptr(rad), knn, ptr(red), ptr(mask),
                                                        _lib.current_stream(device)))
     return red, mask
@@ -273,7 +276,7 @@ def allocate_minimum_redundancy_value(redundancy_values, neighbours_indices, int
     red = redundancy_values.to(device=device, dtype=torch.int32).contiguous()
     nb = neighbours_indices.to(device=device, dtype=torch.int32).contiguous()
     mask = intersection_mask.to(device=device, dtype=torch.bool).contiguous()
-    with torch.cuda.device(device):
+    with on_device(device):
         _lib.check(L.gsb_min_redundancy_value(P, ptr(red), ptr(nb), ptr(mask), knn, ptr(out), _lib.current_stream(device)))
     return (out,)
 
@@ -288,7 +291,7 @@ def kmeans_cuda(values, centers, tol, max_iterations):
     n, k = int(values.size(0)), int(centers.size(0))
     ids = torch.zeros((n, 1), dtype=torch.int32, device=device)
     out = torch.empty((k,), dtype=torch.float32, device=device)
-    with torch.cuda.device(device):
+    with on_device(device):
         ws = torch.empty(int(L.gsb_kmeans_workspace_bytes(n, k)), dtype=torch.uint8, device=device)
         _lib.check(L.gsb_kmeans(ptr(v.reshape(-1)) if n else None, n, ptr(c.reshape(-1)), k, float(tol), int(max_iterations),
                                 ptr(ids), out.data_ptr(), ws.data_ptr(), _lib.current_stream(device)))
@@ -302,7 +305,7 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     present = torch.zeros((P,), dtype=torch.bool, device=device)
     if P:
         m, v, p = f32(means3D, device), f32(viewmatrix, device), f32(projmatrix, device)
-        with torch.cuda.device(device):
+        with on_device(device):
             _lib.check(_lib.lib().gsb_mark_visible(P, ptr(m), ptr(v), ptr(p), present.data_ptr(), _lib.current_stream(device)))
     return present
 
@@ -312,7 +315,7 @@ def export_state(geomBuffer, binningBuffer, imageBuffer, R, W, H, P=0):
     device = imageBuffer.device
     L = _lib.lib()
     out = {}
-    with torch.cuda.device(device):
+    with on_device(device):
         keys = torch.zeros(max(R, 0), dtype=torch.int64, device=device)
         pl = torch.zeros(max(R, 0), dtype=torch.int32, device=device)
         if R > 0:
@@ -335,6 +338,6 @@ def debug_dequant(quant):
     q = _quant_struct(quant, device, keep)
     scales = torch.empty(P, 3, device=device)
     rots = torch.empty(P, 4, device=device)
-    with torch.cuda.device(device):
+    with on_device(device):
         _lib.check(_lib.lib().gsb_debug_dequant(q, P, scales.data_ptr(), rots.data_ptr(), _lib.current_stream(device)))
     return scales, rots

@@ -51,12 +51,10 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
 
     Background tensor (bg_color) must be on GPU!
     """
-    # Create zero tensor. We will use it to make pytorch return gradients of the 2D (screen-space) means
-    screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True, device=pc.get_xyz.device) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+    # Create zero tensor. We will use it to make pytorch return gradients of the 2D (screen-space) means.
+    # (The reference adds 0 to make it a non-leaf and then calls retain_grad(), GR:27-31; a leaf keeps its .grad by itself and
+    # saves an elementwise pass over [P,3].)
+    screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True, device=pc.get_xyz.device)
 
     tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
     tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)

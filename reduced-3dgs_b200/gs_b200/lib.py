@@ -5,8 +5,10 @@ library is missing or no CUDA device is present, calls raise.  PyTorch is used f
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
+import threading
 from typing import Optional
 
 import torch
@@ -187,44 +189,67 @@ def f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
 class BlobAllocator:
     """Python side of gsb_alloc_fn: allocates a torch uint8 tensor (the reference's resizeFunctional,
     rasterize_points.cu:33-41) and keeps it so it can be returned to the caller.
-    The ctypes callback closes over a plain list, NOT over `self`: a bound-method callback would form a reference
-    cycle (self -> cb -> self) and keep the blobs alive until the cyclic GC runs, defeating the caching allocator."""
+
+    The three ctypes callbacks (geometry / binning / image) are created ONCE per host thread and reused by every forward:
+    building a CFUNCTYPE thunk costs ~10-15 us, three of them per call were a tenth of the host time of a step.  A callback
+    closes over this per-thread object only; the tensors of the current call live in `held` and are handed to the caller by
+    `take()`, so nothing keeps a blob alive after the call (no reference cycle through the thunk)."""
 
     # High-water mark of the sizes requested per (device, blob kind).  The instance count R — and with it the binning blob —
     # changes from view to view; requests of slightly different sizes make the caching allocator split / mismatch its cached
     # blocks and fall back to cudaMalloc (1-40 ms, inside a training step) every now and then.  Asking for the largest size
     # seen so far makes every request after the first pass over the views identical, so a freed block always fits.
     _hwm = {}
+    _tls = threading.local()
+    KINDS = ("geom", "binning", "image")
 
-    def __init__(self, device, kind: str = ""):
-        holder = []
-        key = (str(device), kind)
+    def __init__(self):
+        self.device = None
+        self.held = {k: None for k in self.KINDS}
+        self.cb = {k: ALLOC_FN(self._make(k)) for k in self.KINDS}
+
+    @classmethod
+    def for_device(cls, device) -> "BlobAllocator":
+        a = getattr(cls._tls, "alloc", None)
+        if a is None:
+            a = cls._tls.alloc = cls()
+        a.device = device
+        for k in cls.KINDS:
+            a.held[k] = None
+        return a
+
+    def _make(self, kind):
         hwm = BlobAllocator._hwm
 
-        def alloc(_user, nbytes, _holder=holder, _device=device):
+        def alloc(_user, nbytes):
             # round up to 1/16 of the next power of two, then to the high-water mark (unless that is over twice the request:
             # a much smaller workload has started, restart the mark)
             nbytes = int(nbytes)
             if nbytes > (1 << 20):
                 q = 1 << (nbytes.bit_length() - 5)
                 nbytes = (nbytes + q - 1) // q * q
-                if kind:
-                    top = hwm.get(key, 0)
-                    if nbytes <= top <= 2 * nbytes:
-                        nbytes = top
-                    else:
-                        hwm[key] = nbytes
-            t = torch.empty(nbytes, dtype=torch.uint8, device=_device)
-            _holder.append(t)
+                key = (self.device, kind)
+                top = hwm.get(key, 0)
+                if nbytes <= top <= 2 * nbytes:
+                    nbytes = top
+                else:
+                    hwm[key] = nbytes
+            t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.held[kind] = t                     # a second request of the same kind in one call supersedes the first
             return t.data_ptr()
+        return alloc
 
-        self._holder = holder
-        self.cb = ALLOC_FN(alloc)
-        self._empty = torch.empty(0, dtype=torch.uint8, device=device)
+    def take(self, kind):
+        """The blob of `kind` allocated during the call just finished (an empty tensor if the library asked for none)."""
+        t, self.held[kind] = self.held[kind], None
+        return t if t is not None else torch.empty(0, dtype=torch.uint8, device=self.device)
 
-    @property
-    def tensor(self):
-        return self._holder[-1] if self._holder else self._empty
+
+def on_device(device):
+    """Context that makes `device` current for the C-ABI call; free when it already is (the usual case: one process per GPU)."""
+    if torch.cuda.current_device() == device.index:
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
 
 
 def current_stream(device) -> int:
