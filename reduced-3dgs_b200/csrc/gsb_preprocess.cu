@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreArgs a)
 			float4* rec = a.g.rec + 3 * idx;
 			rec[0] = make_float4(conx, cony, conz, pth);
 			rec[1] = make_float4(pix_x, pix_y, opacity, rgb[0]);
-			rec[2] = make_float4(rgb[1], rgb[2], tz, 0.0f);
+			rec[2] = make_float4(rgb[1], rgb[2], tz, __uint_as_float((uint32_t)idx));   // .w: the Gaussian's own id (the backward's flush needs it after the staging buffer is recycled)
 			a.g.clamped[idx] = (uint8_t)clamp_bits;
 			a.g.dbits[idx] = __float_as_uint(tz);
 			if (a.dbg.depths) a.dbg.depths[idx] = tz;

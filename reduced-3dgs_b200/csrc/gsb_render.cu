@@ -14,6 +14,7 @@
 // per-Gaussian sums over a warp's 32 pixels are computed as a small matrix product on the tensor cores (3xTF32
 // mma.sync, see below) and added to the per-Gaussian accumulator with three vector reductions per (warp, Gaussian).
 // The tile's list is staged through a ring of shared-memory buffers filled by TMA bulk copies (mbarrier-tracked).
+#include <cstddef>
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -42,8 +43,15 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
 // STATS = true additionally accumulates, per Gaussian, the number of pixels it contributed to and the sum of the
 // transmittance T in front of it at those pixels (forward.cu:560-564, `calculate_mean_transmittance`): one pair of
 // atomics per (warp, Gaussian) after a ballot / shuffle reduction instead of two per (pixel, Gaussian).
+// Instruction budget (the kernel is issue-bound: ~90 % of the issue slots are busy, ncu).  "This pixel is finished" is the SIGN
+// BIT of T: a finished pixel has T < 0, so its test_T = T * (1 - alpha) <= 0 < 1e-4 takes the reference's stop branch again and
+// changes nothing — no separate flag to carry, turn into a predicate and back on every iteration.  T is carried as its bit pattern
+// (carried as a float, nvcc 12.9 folds the sign-setting arm of the update away — reproduced in isolation — and finished pixels
+// resume).  The two constants of expf's range reduction come from the constant bank (exp_loop).  The per-pair arithmetic is
+// untouched: colours, final_T and n_contrib stay bit-identical.  (A per-warp work queue of surviving entries, which pays off in
+// the backward kernel, was measured here too: its bookkeeping in the cull phase cancelled the gain — forward 0.66 -> 0.68 ms.)
 template <bool STATS>
-__global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __restrict__ ranges,
+__global__ void __launch_bounds__(256, 6) render_forward_kernel(const uint2* __restrict__ ranges,
 	const uint32_t* __restrict__ point_list,
 	int W, int H, const float4* __restrict__ rec, const float* __restrict__ bg,
 	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, uint32_t* __restrict__ tile_max,
@@ -64,12 +72,12 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 	asm volatile("" : "+r"(sbase));                       // keep the shared-window address in a register (otherwise re-derived from SR_CgaCtaId every iteration)
 	if (tid == 0) s_max = 0;
 
-	bool done = !inside;
-	float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
+	uint32_t Tb = inside ? 0x3f800000u : 0xbf800000u;      // bits of T; sign set = finished
+	float C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
 	uint32_t last = 0;
 	for (uint32_t b = range.x; b < range.y; b += 256)
 	{
-		if (__syncthreads_count(done) == 256) break;
+		if (__syncthreads_count((int)Tb < 0) == 256) break;
 		const int n = min(256u, range.y - b);
 		if (tid < n)
 		{
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 			if (STATS) s_id[tid] = id;
 		}
 		__syncthreads();
-		bool warp_done = __all_sync(0xffffffffu, done);
+		bool warp_done = __all_sync(0xffffffffu, (int)Tb < 0);
 		for (int c0 = 0; c0 < n && !warp_done; c0 += 32)
 		{
 			const int j = c0 + lane;
@@ -91,7 +99,8 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 			}
 			unsigned mask = __ballot_sync(0xffffffffu, keep);
 			const uint32_t cbase = sbase + c0 * SREC_BYTES;
-			const uint32_t nbase = (b - range.x) + c0 + 1;          // 1-based list position of the chunk's first entry
+			uint32_t nbase = (b - range.x) + c0 + 1;                // 1-based list position of the chunk's first entry
+			asm volatile("" : "+r"(nbase));                         // (kept in a vector register: `last = nbase + bit` is then one predicated add)
 			// Branch-free per-pixel body: in a surviving warp some lane nearly always takes every path of the reference's
 			// if/continue chain, so predicating costs nothing and removes the divergence bookkeeping.  The arithmetic and
 			// the order of the tests are the reference's (forward.cu:535-569); a masked lane changes no state.
@@ -101,16 +110,16 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 				const uint32_t addr = cbase + bit * SREC_BYTES;
 				const float4 r0 = lds128(addr), r1 = lds128(addr + 16);
 				const float2 gb = lds64(addr + 32);
+				const float T = __uint_as_float(Tb);
 				const float dx = __fsub_rn(r1.x, pxf), dy = __fsub_rn(r1.y, pyf);
 				const float power = pair_power(r0.x, r0.y, r0.z, dx, dy);
 				// power > 0: reference `continue`; power < pth: alpha = opacity*exp(power) is provably < 1/255
-				bool v = !done && !(power > 0.0f) && !(power < r0.w);
-				const float alpha = fminf(0.99f, __fmul_rn(r1.z, exp_ref(power)));
-				v = v && !(alpha < 1.0f / 255.0f);
+				const bool inwin = !(power > 0.0f) && !(power < r0.w);
+				const float alpha = fminf(0.99f, __fmul_rn(r1.z, exp_loop(power)));
+				const bool cand = inwin && !(alpha < 1.0f / 255.0f);
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-				const bool stop = v && (test_T < 0.0001f);
-				done = done || stop;
-				v = v && !stop;
+				const bool stop = cand && (test_T < 0.0001f);           // also true for every finished pixel (T < 0)
+				const bool v = cand && !(test_T < 0.0001f);
 				if (STATS)
 				{
 					const unsigned cm = __ballot_sync(0xffffffffu, v);
@@ -127,15 +136,20 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const uint2* __rest
 						}
 					}
 				}
-				C0 = v ? __fmaf_rn(T, __fmul_rn(r1.w, alpha), C0) : C0;
-				C1 = v ? __fmaf_rn(T, __fmul_rn(gb.x, alpha), C1) : C1;
-				C2 = v ? __fmaf_rn(T, __fmul_rn(gb.y, alpha), C2) : C2;
-				T = v ? test_T : T;
-				last = v ? nbase + bit : last;
+				if (v)
+				{
+					C0 = __fmaf_rn(T, __fmul_rn(r1.w, alpha), C0);
+					C1 = __fmaf_rn(T, __fmul_rn(gb.x, alpha), C1);
+					C2 = __fmaf_rn(T, __fmul_rn(gb.y, alpha), C2);
+					Tb = __float_as_uint(test_T);
+					last = nbase + bit;
+				}
+				if (stop) Tb |= 0x80000000u;
 			}
-			warp_done = __all_sync(0xffffffffu, done);
+			warp_done = __all_sync(0xffffffffu, (int)Tb < 0);
 		}
 	}
+	const float T = __uint_as_float(Tb & 0x7fffffffu);
 	if (inside)
 	{
 		const size_t pid = (size_t)W * py + px, N = (size_t)W * H;
@@ -198,17 +212,28 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 #define BWD_STAGES 4
-struct BwdSmem {
-	float4 rec[BWD_STAGES][BWD_BATCH * 3]; // ring of staged batches of the tile's list: one 48-byte TMA bulk copy per instance
-	uint32_t id[BWD_STAGES][BWD_BATCH];
-	uint64_t full[BWD_STAGES];             // mbarrier: the stage's copies have landed (96 arrivals + transaction bytes)
-	uint64_t empty[BWD_STAGES];            // mbarrier: all 8 warps are done reading the stage
-	float w[8][16 * STASH_LD];
-	float u[8][16 * STASH_LD];
-	uint32_t rowid[8][16];                 // Gaussian id of each stashed row (rows outlive their staging buffer; the flush re-reads the record)
-	float dlp[8][3 * 32];                  // dL/dpixel of the warp's 32 pixels, channel-major: B operand of the colour product
-	float wgt[8 * 32];                     // (1, qx, qy, qx^2, qx*qy, qy^2, 0, 0) of the 32 warp-local pixels: B operand of the moment product
+// Everything one warp owns privately sits in ONE block: a single base address in a register, every member an immediate offset
+// (with separate per-member arrays ptxas re-derived five base addresses inside the hot loop once registers ran out).
+struct BwdWarp {
+	float w[16 * STASH_LD];                // stash of up to 16 surviving Gaussians: w = G * dL/dalpha per pixel lane
+	float u[16 * STASH_LD];                //                                         u = alpha * T per pixel lane
+	float dlp[3 * 32];                     // dL/dpixel of the warp's 32 pixels, channel-major: B operand of the colour product
+	uint32_t rowid[16];                    // Gaussian id of each stashed row (rows outlive their staging buffer; the flush re-reads the record)
+	uint8_t queue[BWD_BATCH + 16];         // work queue: batch indices of the entries that survived the warp's cull (+ slack: the loop reads one ahead)
 };
+#define BW_OFF_U (16 * STASH_LD * 4)
+#define BW_OFF_ROWID (2 * 16 * STASH_LD * 4 + 3 * 32 * 4)
+#define BW_OFF_QUEUE (BW_OFF_ROWID + 16 * 4)
+struct BwdSmem {
+	float4 rec[BWD_STAGES][BWD_BATCH * 3]; // ring of staged batches of the tile's list: one 48-byte TMA bulk copy per instance (the record carries its Gaussian id in r2.w)
+	uint64_t full[BWD_STAGES];             // mbarrier: the stage's copies have landed (64 arrivals + transaction bytes)
+	uint64_t empty[BWD_STAGES];            // mbarrier: all 8 warps are done reading the stage
+	float wgt[8 * 32];                     // (1, qx, qy, qx^2, qx*qy, qy^2, 0, 0) of the 32 warp-local pixels: B operand of the moment product
+	BwdWarp wp[8];
+};
+static_assert(offsetof(BwdWarp, u) == BW_OFF_U && offsetof(BwdWarp, rowid) == BW_OFF_ROWID && offsetof(BwdWarp, queue) == BW_OFF_QUEUE, "BwdWarp layout");
+static_assert(sizeof(BwdWarp) % 16 == 0, "BwdWarp alignment");
+
 
 __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __restrict__ ranges,
 	const uint32_t* __restrict__ point_list,
@@ -232,6 +257,10 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 	const size_t pid = (size_t)W * py + px, N = (size_t)W * H;
 	uint32_t sbase0 = (uint32_t)__cvta_generic_to_shared(&S.rec[0][0]);
 	asm volatile("" : "+r"(sbase0));
+	BwdWarp& Wp = S.wp[warp];
+	uint32_t wbase = (uint32_t)__cvta_generic_to_shared(&Wp);           // the warp's private block (see BwdWarp)
+	asm volatile("" : "+r"(wbase));
+	const unsigned lt_mask = (1u << lane) - 1u;
 
 	const float T_final = inside ? final_Ts[pid] : 0.0f;
 	float T = T_final;
@@ -247,8 +276,8 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 	// B fragments (m16n8k8: b0 = B[k = t][n = g], b1 = B[k = t + 4][n = g]; k = pixel lane of the k-step, n = output column) are
 	// rebuilt inside flush_rows (a few shuffles per 16 Gaussians) instead of living in 24 registers: occupancy matters more.
 	const int fg = lane >> 2, ft = lane & 3;
-	float* sw = S.w[warp];
-	float* su = S.u[warp];
+	float* sw = Wp.w;
+	float* su = Wp.u;
 	uint32_t nrows = 0;                                                           // warp-uniform: stashed Gaussians
 	int buf = 0;
 
@@ -262,7 +291,7 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 		S.wgt[3 * 32 + tid] = qx * qx; S.wgt[4 * 32 + tid] = qx * qy; S.wgt[5 * 32 + tid] = qy * qy;
 		S.wgt[6 * 32 + tid] = 0.0f; S.wgt[7 * 32 + tid] = 0.0f;
 	}
-	S.dlp[warp][lane] = dLp0; S.dlp[warp][32 + lane] = dLp1; S.dlp[warp][64 + lane] = dLp2;
+	Wp.dlp[lane] = dLp0; Wp.dlp[32 + lane] = dLp1; Wp.dlp[64 + lane] = dLp2;
 	const float cxw = rx0 + 3.5f, cyw = ry0 + 1.5f;                                // centre of the warp's 8x4 pixel block
 	__syncthreads();
 
@@ -275,11 +304,11 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 		__syncwarp();
 		if (ft == 0)                                                                 // the epilogue re-reads the rows' records: pull them into L1 behind the MMAs
 		{
-			if (fg < nrows) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 3 * (size_t)S.rowid[warp][fg]));
-			if (fg + 8 < nrows) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 3 * (size_t)S.rowid[warp][fg + 8]));
+			if (fg < nrows) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 3 * (size_t)Wp.rowid[fg]));
+			if (fg + 8 < nrows) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 3 * (size_t)Wp.rowid[fg + 8]));
 		}
 		float dw[4] = { 0.f, 0.f, 0.f, 0.f }, du[4] = { 0.f, 0.f, 0.f, 0.f };
-		const float* dl = S.dlp[warp] + (fg < 3 ? fg : 0) * 32;
+		const float* dl = Wp.dlp + (fg < 3 ? fg : 0) * 32;
 #pragma unroll
 		for (int kk = 0; kk < 4; kk++)
 		{
@@ -312,7 +341,7 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 			const uint32_t row = fg + 8 * h;
 			if (ft == 0 && row < nrows)
 			{
-				const uint32_t gid = S.rowid[warp][row];
+				const uint32_t gid = Wp.rowid[row];
 				const float4 r0 = __ldg(rec + 3 * (size_t)gid), r1 = __ldg(rec + 3 * (size_t)gid + 1);      // L2-resident: staged moments ago
 				const float X = r1.x - cxw, Y = r1.y - cyw, o = r1.z;
 				const float M0 = dw[2 * h], Mx = dw[2 * h + 1];
@@ -341,7 +370,6 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 		const int st = bi % BWD_STAGES;
 		if (id != 0xffffffffu)
 		{
-			S.id[st][tid] = id;
 			mbar_arrive_expect_tx(&S.full[st], 48u);
 			tma_bulk_g2s(&S.rec[st][3 * tid], rec + 3 * (size_t)id, 48u, &S.full[st]);
 		}
@@ -374,6 +402,8 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 		}
 		mbar_wait(&S.full[buf], (bi / BWD_STAGES) & 1u);
 		const uint32_t sbase = sbase0 + (uint32_t)(buf * BWD_BATCH * 3) * 16u;
+		// ---- cull the batch into the warp's work queue (see render_forward_kernel) ----
+		uint32_t qn = 0;
 		for (int c0 = 0; c0 < n; c0 += 32)
 		{
 			const int j = c0 + lane;
@@ -383,44 +413,56 @@ __global__ void __launch_bounds__(256, 4) render_backward_kernel(const uint2* __
 				const float4 r0 = lds128(sbase + j * SREC_BYTES), r1 = lds128(sbase + j * SREC_BYTES + 16);
 				keep = rect_may_contribute(r1.x, r1.y, r0.x, r0.y, r0.z, r0.w, rx0, rx1, ry0, ry1);
 			}
-			unsigned mask = __ballot_sync(0xffffffffu, keep);
-			while (mask)
+			const unsigned mask = __ballot_sync(0xffffffffu, keep);
+			if (keep) Wp.queue[qn + __popc(mask & lt_mask)] = (uint8_t)j;
+			qn += __popc(mask);
+		}
+		__syncwarp();
+		uint32_t posb = hi - 1 - b;                                            // list position of batch entry 0 (entries run backwards)
+		asm volatile("" : "+r"(posb));
+		uint32_t jj = 0, jnext;
+		if (qn) asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(jj) : "r"(wbase), "n"(BW_OFF_QUEUE));
+		for (uint32_t q = 0; q < qn; q++, jj = jnext)
+		{
+			asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(jnext) : "r"(wbase + q), "n"(BW_OFF_QUEUE + 1));   // next entry's index: off the critical path
+			const uint32_t pos = posb - jj;
+			const uint32_t addr = sbase + jj * SREC_BYTES;
+			const float4 r0 = lds128(addr), r1 = lds128(addr + 16);
+			const float dx = __fsub_rn(r1.x, pxf), dy = __fsub_rn(r1.y, pyf);
+			const float power = pair_power(r0.x, r0.y, r0.z, dx, dy);
+			const float G = exp_loop(power);
+			const float alpha = fminf(0.99f, __fmul_rn(r1.z, G));
+			// backward.cu:524-539: same skips as the forward (pos < last_contributor replaces the `contributor` countdown)
+			const bool active = (pos < last_contributor) && !(power > 0.0f) && !(power < r0.w) && !(alpha < 1.0f / 255.0f);
+			if (!__any_sync(0xffffffffu, active)) continue;
+			float wv = 0.f, uv = 0.f;
+			const float4 r2 = lds128(addr + 32);                               // (G, B, depth, Gaussian id)
+			if (active)
 			{
-				const int jj = c0 + __ffs(mask) - 1; mask &= mask - 1;
-				const uint32_t pos = hi - 1 - b - jj;
-				const uint32_t addr = sbase + jj * SREC_BYTES;
-				const float4 r0 = lds128(addr), r1 = lds128(addr + 16);
-				const float dx = __fsub_rn(r1.x, pxf), dy = __fsub_rn(r1.y, pyf);
-				const float power = pair_power(r0.x, r0.y, r0.z, dx, dy);
-				const float G = exp_ref(power);
-				const float alpha = fminf(0.99f, __fmul_rn(r1.z, G));
-				// backward.cu:524-539: same skips as the forward (pos < last_contributor replaces the `contributor` countdown)
-				const bool active = (pos < last_contributor) && !(power > 0.0f) && !(power < r0.w) && !(alpha < 1.0f / 255.0f);
-				if (!__any_sync(0xffffffffu, active)) continue;
-				float wv = 0.f, uv = 0.f;
-				if (active)
-				{
-					const float inv = __frcp_rn(1.0f - alpha);
-					T = T * inv;                                                        // backward.cu:541
-					uv = alpha * T;
-					const float2 gb = lds64(addr + 32);
-					const float cr = r1.w, cg = gb.x, cb = gb.y;
-					const float oml = 1.0f - last_alpha;
-					ar0 = last_alpha * lc0 + oml * ar0; lc0 = cr;
-					ar1 = last_alpha * lc1 + oml * ar1; lc1 = cg;
-					ar2 = last_alpha * lc2 + oml * ar2; lc2 = cb;
-					float dL_dalpha = (cr - ar0) * dLp0 + (cg - ar1) * dLp1 + (cb - ar2) * dLp2;
-					dL_dalpha *= T;
-					last_alpha = alpha;
-					dL_dalpha += (-T_final * inv) * bg_dot_dpixel;                      // backward.cu:569-572
-					wv = G * dL_dalpha;
-				}
-				sw[nrows * STASH_LD + lane] = wv;
-				su[nrows * STASH_LD + lane] = uv;
-				if (lane == 0) S.rowid[warp][nrows] = S.id[buf][jj];
-				nrows++;
-				if (nrows == 16) flush_rows();
+				// backward.cu:541 T = T / (1 - alpha): 1 - alpha lies in [0.01, 1], MUFU.RCP (1 ulp) is ample for a gradient that is
+				// tolerance-compared; the IEEE-rounded reciprocal costs 12 more instructions per pair (range check + Newton step)
+				const float inv = rcp_approx(1.0f - alpha);
+				T = T * inv;
+				uv = alpha * T;
+				const float cr = r1.w, cg = r2.x, cb = r2.y;
+				const float oml = 1.0f - last_alpha;
+				ar0 = last_alpha * lc0 + oml * ar0; lc0 = cr;
+				ar1 = last_alpha * lc1 + oml * ar1; lc1 = cg;
+				ar2 = last_alpha * lc2 + oml * ar2; lc2 = cb;
+				float dL_dalpha = (cr - ar0) * dLp0 + (cg - ar1) * dLp1 + (cb - ar2) * dLp2;
+				dL_dalpha *= T;
+				last_alpha = alpha;
+				dL_dalpha += (-T_final * inv) * bg_dot_dpixel;                      // backward.cu:569-572
+				wv = G * dL_dalpha;
 			}
+			{
+				const uint32_t sa = wbase + (nrows * STASH_LD + lane) * 4;
+				asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa), "f"(wv) : "memory");
+				asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(sa), "f"(uv), "n"(BW_OFF_U) : "memory");
+				if (lane == 0) asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(wbase + nrows * 4), "f"(r2.w), "n"(BW_OFF_ROWID) : "memory");
+			}
+			nrows++;
+			if (nrows == 16) flush_rows();
 		}
 		__syncwarp();
 		if (lane == 0) mbar_arrive(&S.empty[buf]);           // this warp no longer reads the stage (stashed rows carry their own data)
