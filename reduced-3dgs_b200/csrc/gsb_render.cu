@@ -15,6 +15,7 @@
 // mma.sync, see below) and added to the per-Gaussian accumulator with three vector reductions per (warp, Gaussian).
 // The tile's list is staged through a ring of shared-memory buffers filled by TMA bulk copies (mbarrier-tracked).
 #include <cstddef>
+#include <cstdlib>
 #include "gsb_common.cuh"
 
 namespace gsb {
@@ -48,8 +49,14 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
 // changes nothing — no separate flag to carry, turn into a predicate and back on every iteration.  T is carried as its bit pattern
 // (carried as a float, nvcc 12.9 folds the sign-setting arm of the update away — reproduced in isolation — and finished pixels
 // resume).  The two constants of expf's range reduction come from the constant bank (exp_loop).  The per-pair arithmetic is
-// untouched: colours, final_T and n_contrib stay bit-identical.  (A per-warp work queue of surviving entries, which pays off in
-// the backward kernel, was measured here too: its bookkeeping in the cull phase cancelled the gain — forward 0.66 -> 0.68 ms.)
+// untouched: colours, final_T and n_contrib stay bit-identical.
+// What bounds this kernel (ncu, 3 M Gaussians / 1080p): the FP32 pipe.  ~28 FADD/FMUL/FFMA-class warp instructions per (warp,
+// entry) x 10.5 M iterations + the cull arithmetic = ~350 M fp32 warp instructions; the pipe takes one every other cycle per
+// sub-partition (`sm__pipe_fma_cycles_active` sits at 50 % in every variant) = 0.60 ms of the measured 0.655 ms.  Three variants
+// confirmed it (all bit-identical, all within 4 % of each other): this one (48 instructions per entry instead of 52: same time,
+// issue slots 89 -> 84 %); a per-warp work queue as in the backward (45 per entry, but its cull-phase bookkeeping cost as much);
+// and packed FFMA2 over two consecutive entries (34 per entry, 36 % fewer fp32 instructions — but an FFMA2 holds the pipe for
+// two passes: pipe cycles unchanged, 0.68 ms).  The kernel is at the fp32 roofline of the reference's per-pair arithmetic.
 template <bool STATS>
 __global__ void __launch_bounds__(256, 6) render_forward_kernel(const uint2* __restrict__ ranges,
 	const uint32_t* __restrict__ point_list,
