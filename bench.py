@@ -445,8 +445,15 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
     copy_done = torch.cuda.Event()
     G_dev = torch.empty_like(G_host, device=dev)
 
-    def h2d_side(src):
-        side.wait_stream(torch.cuda.current_stream())      # the previous step has consumed G_dev, and the timed region has started
+    step_start = torch.cuda.Event()
+
+    def h2d_side(src, after_current=True):
+        # the copy may not start before the previous step has consumed G_dev and the timed region has begun (`step_start`, recorded
+        # on the main stream at the top of every step); it does not wait for the forward that was just enqueued
+        if after_current:
+            side.wait_stream(torch.cuda.current_stream())
+        else:
+            side.wait_event(step_start)
         with torch.cuda.stream(side):
             G_dev.copy_(src, non_blocking=True)
             copy_done.record(side)
@@ -458,8 +465,8 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
 
         def one(i):
             v = my_views[i % len(my_views)]
+            step_start.record()
             cm = cam_host[v].to(dev, non_blocking=True)
-            Gd = h2d_side(G_host)                      # dL/dimage is only needed by the backward: copied on a side stream under the forward
             cam = SimpleNamespace(FoVx=cams[v].FoVx, FoVy=cams[v].FoVy, image_height=H, image_width=W,
                                   world_view_transform=cm[:16].view(4, 4), full_proj_transform=cm[16:32].view(4, 4),
                                   camera_center=cm[32:35])
@@ -467,6 +474,9 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
                 for p in pc.params():
                     p.grad = None
             pkg = render(cam, pc, pipe, bg)
+            # dL/dimage is only needed by the backward: its 24.9 MB copy is enqueued on a side stream once the forward is launched and
+            # runs under it (both arms; enqueueing it first delays the forward's first kernel by the copy call's host time)
+            Gd = h2d_side(G_host, after_current=False)
             torch.cuda.current_stream().wait_event(copy_done)
             loss = (pkg["render"] * Gd).sum()
             loss.backward()
@@ -487,11 +497,12 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
 
         def one(i):
             v = my_views[i % len(my_views)]
+            step_start.record()
             cm = cam_host[v].to(dev, non_blocking=True)
-            Gd = h2d_side(G_host)
             a = (bg, sd.means3D, EMPTY, sd.opacity, sd.scales, sd.rotations, 1.0, EMPTY, cm[:16].view(4, 4).contiguous(),
                  cm[16:32].view(4, 4).contiguous(), tanx[v], tany[v], H, W, sd.sh, sd.degrees, cm[32:35].contiguous(), False, False)
             R, color, radii, gb, bb, ib = refC.rasterize_gaussians(*a)
+            Gd = h2d_side(G_host, after_current=False)
             torch.cuda.current_stream().wait_event(copy_done)
             loss = (color * Gd).sum()
             refC.rasterize_gaussians_backward(bg, sd.means3D, radii, EMPTY, sd.scales, sd.rotations, 1.0, EMPTY, a[8], a[9], a[10],

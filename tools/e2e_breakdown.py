@@ -1,4 +1,4 @@
-"""Where does the end-to-end step go?  Variants of bench.py's e2e loop (C2), each timed with CUDA events over 20 steps."""
+"""Where does the end-to-end step go?  Variants of bench.py's e2e loop (config = argv[1], default C2), each timed with CUDA events over 20 steps."""
 import math, os, sys, time
 from types import SimpleNamespace
 import torch
@@ -9,14 +9,14 @@ from gs_b200 import synth
 from gaussian_renderer import render
 
 dev = torch.device("cuda", 0)
-W, H = synth.config_image("C2")
-scene = synth.config_scene("C2")
+CFG = sys.argv[1] if len(sys.argv) > 1 else "C2"
+_name, W, H, scene, quant, _prune = bench.build_workload(SimpleNamespace(config=CFG, points=0), dev, 0, 1)
 cams = [c.to(dev) for c in bench.bench_cameras(W, H, 4)]
 G_host = synth.grad_image(W, H, 1000).pin_memory()
 G_res = G_host.to(dev)
 bg = torch.zeros(3, device=dev)
 pipe = SimpleNamespace(debug=False, convert_SHs_python=False, compute_cov3D_python=False)
-pc = bench.ModelView(scene, dev, None, None)
+pc = bench.ModelView(scene, dev, None if quant is None else quant.to(dev), None)
 cam_host = [torch.cat([c.world_view_transform.flatten(), c.full_proj_transform.flatten(), c.camera_center.flatten()]).cpu().pin_memory() for c in cams]
 side = torch.cuda.Stream(device=dev); copy_done = torch.cuda.Event(); G_dev = torch.empty_like(G_host, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
