@@ -57,6 +57,10 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
 // issue slots 89 -> 84 %); a per-warp work queue as in the backward (45 per entry, but its cull-phase bookkeeping cost as much);
 // and packed FFMA2 over two consecutive entries (34 per entry, 36 % fewer fp32 instructions — but an FFMA2 holds the pipe for
 // two passes: pipe cycles unchanged, 0.68 ms).  The kernel is at the fp32 roofline of the reference's per-pair arithmetic.
+// Staging: the batch is gathered with three 128-bit loads per thread and stored to shared memory.  The TMA path of the backward
+// (one cp.async.bulk per 48-byte record, completion on an mbarrier) was measured here as well: 0.73 ms single-buffered, 0.75 ms with
+// a two-deep ring (vs 0.66 ms) — 256 small copies per batch serialise in the copy engine, while the load/store path issues them
+// from 256 threads at once and this kernel has no other use for the time a ring would hide.
 template <bool STATS>
 __global__ void __launch_bounds__(256, 6) render_forward_kernel(const uint2* __restrict__ ranges,
 	const uint32_t* __restrict__ point_list,
