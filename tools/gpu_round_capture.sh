@@ -1,13 +1,16 @@
-# Round capture on the GPU box: both bench arms (C2 default, C3), ncu launch lists and one --set full pass per kernel.
-# Output (gpurun_out/) must stay under 64 MiB: one captured step per config.
+# Round-2 evidence capture on the GPU box (one GPU): both bench arms at the default config (C3), C2 / C4 / C5 for the tables,
+# ncu launch lists and one `--set full` pass per kernel for C2 / C3 / C5.  gpurun_out/ must stay under 64 MiB.
 set -x
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
-timeout 600 python bench.py --impl reference > gpurun_out/bench_default_ref.json 2> gpurun_out/bench_default_ref.err
-timeout 600 python bench.py --config C3 --no-cpu-baseline > gpurun_out/bench_ours_C3.json 2> gpurun_out/bench_ours_C3.err
-timeout 600 python bench.py --config C3 --impl reference > gpurun_out/bench_ref_C3.json 2> gpurun_out/bench_ref_C3.err
-for c in C2 C3; do
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r1_launches_$c.csv python bench.py --config $c --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1_launches_$c.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"render_|tile_sort|preprocess|scatter|tile_prefix|tile_scan" -s 99 -c 9 -f -o gpurun_out/r1_full_$c python bench.py --config $c --steps 3 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r1_full_$c.log 2>&1
+R=${ROUND:-r2}
+timeout 600 python bench.py > gpurun_out/${R}_bench_default.json 2> gpurun_out/${R}_bench_default.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference > gpurun_out/${R}_bench_default_ref.json 2> gpurun_out/${R}_bench_default_ref.err
+for c in C2 C4 C5; do
+timeout 900 python bench.py --config $c --no-cpu-baseline > gpurun_out/${R}_bench_ours_$c.json 2> gpurun_out/${R}_bench_ours_$c.err
+timeout 900 python bench.py --config $c --impl reference > gpurun_out/${R}_bench_ref_$c.json 2> gpurun_out/${R}_bench_ref_$c.err
 done
-ls -la gpurun_out/
+for c in C3 C2 C5; do
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${R}_launches_$c.csv python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${R}_launches_$c.log 2>&1
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"render_|tile_sort_dist|preprocess|scatter|tile_prefix|tile_scan" -s 32 -c 8 -f -o gpurun_out/${R}_full_$c python bench.py --config $c --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/${R}_full_$c.log 2>&1
+done
+ls -la gpurun_out/ | tail -30
