@@ -130,6 +130,29 @@ __device__ __forceinline__ void st_u64_policy(uint64_t* p, uint64_t v, uint64_t 
 	asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
 }
 
+// Row-band launches (bucket array larger than L2): the slice of the bucket array that belongs to the tile rows of one band is
+// pre-written with full-sector stores right before that band's scatter (see scatter_prefill).  The slice's bounds are device
+// data (`ranges` of the band's first / last non-empty tile), hence a kernel and not a memset.
+__global__ void __launch_bounds__(256) band_prefill_kernel(const uint2* __restrict__ ranges, int t0, int t1, uint64_t* __restrict__ bucket,
+	const uint32_t* __restrict__ counters, uint32_t cap)
+{
+	if (counters[0] > cap) return;                   // speculative launch, see scatter_priv_kernel
+	__shared__ uint32_t s_lo, s_hi;
+	if (threadIdx.x == 0)
+	{
+		uint32_t lo = 0, hi = 0;
+		for (int t = t0; t < t1; t++) { const uint2 r = ranges[t]; if (r.y > r.x) { lo = r.x; break; } }
+		for (int t = t1 - 1; t >= t0; t--) { const uint2 r = ranges[t]; if (r.y > r.x) { hi = r.y; break; } }
+		s_lo = lo; s_hi = hi;
+	}
+	__syncthreads();
+	const uint32_t lo = (s_lo + 1u) & ~1u, hi = s_hi & ~1u;      // 16-byte aligned interior; the two edge entries are written by the scatter anyway
+	if (hi <= lo) return;
+	uint4* p = reinterpret_cast<uint4*>(bucket + lo);
+	const size_t n16 = (size_t)(hi - lo) / 2;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // Scatter with privatised cursors: CTA c (same Gaussian chunk as in the preprocess kernel) starts every tile's cursor at
 // tile start + (instances of that tile owned by CTAs < c); slots are then claimed with shared-memory atomics only.
 __global__ void __launch_bounds__(1024, 1) scatter_priv_kernel(int P, int chunk, int T, const uint32_t* __restrict__ depth_bits, const uint2* __restrict__ rect,
@@ -567,7 +590,11 @@ int launch_scatter_sort(const GeomState& g, const BinningState& b, const ImageSt
 			for (int y0 = 0; y0 < gy; y0 += rows)
 			{
 				const int y1 = std::min(gy, y0 + rows);
-				if (scatter_prefill() && bands == 1) GSB_CUDA_OK(cudaMemsetAsync(b.bucket, 0, size_t(cap) * 8, stream));
+				if (scatter_prefill())
+				{
+					if (bands == 1) GSB_CUDA_OK(cudaMemsetAsync(b.bucket, 0, size_t(cap) * 8, stream));
+					else { band_prefill_kernel<<<148 * 2, 256, 0, stream>>>(img.ranges, y0 * gx, y1 * gx, b.bucket, g.counters, cap32); GSB_LAUNCHED(); }
+				}
 				scatter_priv_kernel<<<plan.ctas, plan.threads, size_t(y1 - y0) * gx * sizeof(uint32_t), stream>>>(P, plan.chunk, T, g.dbits, g.rect,
 					img.ranges, img.cta_count, gx, (uint32_t)y0, (uint32_t)y1, b.bucket, g.counters, cap32);
 				GSB_LAUNCHED();
