@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __rest
 	if (counters[0] > cap) return;                   // speculative launch, see scatter_priv_kernel
 	__shared__ uint32_t s_bin[DIST_BINS];
 	__shared__ __align__(16) uint64_t s_out[GSB_SORT_CAP_A];
+	__shared__ __align__(16) uint32_t s_rank[GSB_SORT_CAP_A];          // the sorted ids, written by rank
 	__shared__ uint32_t s_wtot[8];
 	__shared__ uint32_t s_min, s_max, s_big;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -465,25 +466,28 @@ __global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __rest
 		if (p < n) s_out[s_bin[slot[i] >> 16] + (slot[i] & 0xffffu)] = c[i];
 	}
 	__syncthreads();
-	// finish each of this thread's bins (ascending composite = depth bits, then Gaussian id)
-	{
-		uint32_t run = start;
+	// Finish the bins by RANK, one entry at a time: an entry's final position is its bin's start + the number of bin-mates with a
+	// smaller composite (depth bits, then Gaussian id; composites are unique).  The earlier version let each thread insertion-sort
+	// the 8 bins it owned: 40 % of the kernel's stall samples were the barrier behind that loop (a thread that owns a crowded bin
+	// holds up the CTA).  Ranking costs the same comparisons but spreads a crowded bin's work over the threads that hold its
+	// entries (entries are dealt round-robin).
+	uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_rank);
 #pragma unroll
-		for (int i = 0; i < 8; i++)
+	for (int i = 0; i < 8; i++)
+	{
+		const uint32_t p = i * 256 + tid;
+		if (p < n)
 		{
-			const uint32_t m = cnt[i];
-			for (uint32_t a = 1; a < m; a++)
-			{
-				const uint64_t v = s_out[run + a];
-				uint32_t j = a;
-				while (j > 0 && s_out[run + j - 1] > v) { s_out[run + j] = s_out[run + j - 1]; j--; }
-				s_out[run + j] = v;
-			}
-			run += m;
+			const uint32_t b = slot[i] >> 16;
+			const uint32_t start = s_bin[b], end = (b + 1 < DIST_BINS) ? s_bin[b + 1] : n;
+			const uint64_t v = c[i];
+			uint32_t rank = 0;
+			for (uint32_t k = start; k < end; k++) rank += s_out[k] < v ? 1u : 0u;
+			s_sorted[start + rank] = (uint32_t)v;
 		}
 	}
 	__syncthreads();
-	for (uint32_t i = tid; i < n; i += 256) point_list[r.x + i] = (uint32_t)s_out[i];
+	for (uint32_t i = tid; i < n; i += 256) point_list[r.x + i] = s_sorted[i];
 }
 
 // Segments beyond the shared-memory classes: single-CTA stable LSD radix sort (8 x 8-bit digits of the 64-bit

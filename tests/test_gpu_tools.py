@@ -166,7 +166,9 @@ def _kmeans_checks(c, v, centers, ref):
     assert np.array_equal(ids0.cpu().numpy(), ref["ids_iter0"])
     # (2) one iteration: same partition -> same sizes, centres equal up to float summation order
     ids1, c1 = C.kmeans_cuda(vd, cd, 0.0, 1)
-    assert np.abs(c1.cpu().numpy() - ref["centers_iter1"]).max() <= 2e-6 * (np.abs(ref["centers_iter1"]).max() + 1e-30) + 1e-7
+    # (both sides add ~6 000 floats per centre with float atomics in an arbitrary order: a few 1e-6 relative is their own run-to-run
+    # noise — a 2e-6 bound here failed about one run in five against the LIVE reference)
+    assert np.abs(c1.cpu().numpy() - ref["centers_iter1"]).max() <= 2e-5 * (np.abs(ref["centers_iter1"]).max() + 1e-30) + 1e-6
     mism = (ids1.cpu().numpy() != ref["ids_iter1"]).mean()
     assert mism <= 1e-4, mism                                    # a value within an ulp of a boundary may flip with the summation order
     # (3) to convergence: the returned ids are EXACTLY the assignment for the returned centres, and the quantisation cost
