@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 	__shared__ uint32_t s_warp[32];
 	__shared__ unsigned long long s_carry;            // 64-bit: a total beyond 2^32 must not wrap silently
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) { s_carry = 0; cls_count[0] = 0; cls_count[1] = 0; cls_count[2] = 0; }
+	if (tid == 0) { s_carry = 0; cls_count[0] = 0; cls_count[1] = 0; cls_count[2] = 0; cls_count[3] = 0; }
 	__syncthreads();
 	for (int base = 0; base < T; base += 1024)
 	{
@@ -390,80 +390,84 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint2* __restr
 // narrow range, so binning them by (key - min) >> shift into 2048 order-preserving bins leaves ~1 key per bin; a per-bin
 // insertion sort on the full 64-bit composite (depth bits, id) then finishes the total order.  Tiles whose depths cluster
 // (some bin > 32 keys) are flagged and handled by the radix kernel below, so the result never depends on the heuristic.
-#define DIST_BINS 2048
-__global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
-	uint32_t* __restrict__ point_list, uint32_t* __restrict__ fallback_list, uint32_t* __restrict__ fallback_count,
-	const uint32_t* __restrict__ counters, uint32_t cap)
+// One template serves both shared-memory classes: THREADS = 256 sorts tiles of up to 2048 instances (one CTA per tile,
+// 2048 bins), THREADS = 1024 tiles of up to 8192 instances (persistent CTAs over the queued tile list, 8192 bins).
+template <int THREADS>
+struct DistSmem {
+	static constexpr int CAP = 8 * THREADS, BINS = 8 * THREADS;
+	uint64_t out[CAP];                   // entries grouped by bin (unsorted inside a bin)
+	uint32_t bin[BINS];                  // counts, then exclusive starts
+	uint32_t sorted[CAP];                // the sorted ids, written by rank
+	uint32_t wtot[32];
+	uint32_t kmin, kmax, big;
+};
+
+template <int THREADS>
+__device__ __forceinline__ void dist_sort_tile(DistSmem<THREADS>& S, uint32_t tile, const uint2 r, const uint64_t* __restrict__ bucket,
+	uint32_t* __restrict__ point_list, uint32_t* __restrict__ fallback_list, uint32_t* __restrict__ fallback_count)
 {
-	if (counters[0] > cap) return;                   // speculative launch, see scatter_priv_kernel
-	__shared__ uint32_t s_bin[DIST_BINS];
-	__shared__ __align__(16) uint64_t s_out[GSB_SORT_CAP_A];
-	__shared__ __align__(16) uint32_t s_rank[GSB_SORT_CAP_A];          // the sorted ids, written by rank
-	__shared__ uint32_t s_wtot[8];
-	__shared__ uint32_t s_min, s_max, s_big;
+	constexpr int BINS = DistSmem<THREADS>::BINS, NW = THREADS / 32;
+	constexpr int LOG_BINS = THREADS == 256 ? 11 : 13;
+	static_assert(THREADS == 256 || THREADS == 1024, "bin count = 8 * THREADS must be 2^LOG_BINS");
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t tile = blockIdx.x;
-	const uint2 r = ranges[tile];
 	const uint32_t n = r.y - r.x;
-	if (n == 0 || n > GSB_SORT_CAP_A) return;
-	if (n == 1) { if (tid == 0) point_list[r.x] = (uint32_t)bucket[r.x]; return; }
-	if (tid == 0) { s_min = 0xffffffffu; s_max = 0u; s_big = 0u; }
-	for (int i = tid; i < DIST_BINS; i += 256) s_bin[i] = 0;
+	if (tid == 0) { S.kmin = 0xffffffffu; S.kmax = 0u; S.big = 0u; }
+	for (int i = tid; i < BINS; i += THREADS) S.bin[i] = 0;
 	__syncthreads();
 	uint64_t c[8];
 	uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
 	for (int i = 0; i < 8; i++)
 	{
-		const uint32_t p = i * 256 + tid;
+		const uint32_t p = i * THREADS + tid;
 		c[i] = p < n ? bucket[r.x + p] : ~0ull;
 		if (p < n) { const uint32_t k = (uint32_t)(c[i] >> 32); kmin = min(kmin, k); kmax = max(kmax, k); }
 	}
 	kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
-	if (lane == 0) { atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+	if (lane == 0) { atomicMin(&S.kmin, kmin); atomicMax(&S.kmax, kmax); }
 	__syncthreads();
-	const uint32_t lo = s_min, range = s_max - lo;
-	const int shift = max(0, (32 - __clz(range)) - 11);              // (range >> shift) < 2048
+	const uint32_t lo = S.kmin, range = S.kmax - lo;
+	const int shift = max(0, (32 - __clz(range)) - LOG_BINS);        // (range >> shift) < BINS
 	uint32_t slot[8];
 	uint32_t worst = 0;
 #pragma unroll
 	for (int i = 0; i < 8; i++)
 	{
-		const uint32_t p = i * 256 + tid;
+		const uint32_t p = i * THREADS + tid;
 		if (p < n)
 		{
 			const uint32_t b = ((uint32_t)(c[i] >> 32) - lo) >> shift;
-			const uint32_t q = atomicAdd(&s_bin[b], 1u);
+			const uint32_t q = atomicAdd(&S.bin[b], 1u);
 			slot[i] = (b << 16) | q;
 			worst = max(worst, q);
 		}
 	}
-	if (__any_sync(0xffffffffu, worst >= 32)) { if (lane == 0) s_big = 1; }
+	if (__any_sync(0xffffffffu, worst >= 32)) { if (lane == 0) S.big = 1; }
 	__syncthreads();
-	if (s_big) { if (tid == 0) fallback_list[atomicAdd(fallback_count, 1u)] = tile; return; }   // queued for the radix kernel
-	// exclusive scan of the 2048 bin counts: thread t owns bins [8t, 8t+8)
+	if (S.big) { if (tid == 0) fallback_list[atomicAdd(fallback_count, 1u)] = tile; return; }   // queued for the radix kernel
+	// exclusive scan of the bin counts: thread t owns bins [8t, 8t+8)
 	uint32_t cnt[8], local = 0;
 #pragma unroll
-	for (int i = 0; i < 8; i++) { cnt[i] = s_bin[8 * tid + i]; local += cnt[i]; }
+	for (int i = 0; i < 8; i++) { cnt[i] = S.bin[8 * tid + i]; local += cnt[i]; }
 	uint32_t incl = local;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-	if (lane == 31) s_wtot[warp] = incl;
+	if (lane == 31) S.wtot[warp] = incl;
 	__syncthreads();
 	uint32_t start = incl - local;
 #pragma unroll
-	for (int w = 0; w < 8; w++) if (w < warp) start += s_wtot[w];
+	for (int w = 0; w < NW; w++) if (w < warp) start += S.wtot[w];
 	{
 		uint32_t run = start;
 #pragma unroll
-		for (int i = 0; i < 8; i++) { s_bin[8 * tid + i] = run; run += cnt[i]; }
+		for (int i = 0; i < 8; i++) { S.bin[8 * tid + i] = run; run += cnt[i]; }
 	}
 	__syncthreads();
 #pragma unroll
 	for (int i = 0; i < 8; i++)
 	{
-		const uint32_t p = i * 256 + tid;
-		if (p < n) s_out[s_bin[slot[i] >> 16] + (slot[i] & 0xffffu)] = c[i];
+		const uint32_t p = i * THREADS + tid;
+		if (p < n) S.out[S.bin[slot[i] >> 16] + (slot[i] & 0xffffu)] = c[i];
 	}
 	__syncthreads();
 	// Finish the bins by RANK, one entry at a time: an entry's final position is its bin's start + the number of bin-mates with a
@@ -471,23 +475,55 @@ __global__ void __launch_bounds__(256) tile_sort_dist_kernel(const uint2* __rest
 	// the 8 bins it owned: 40 % of the kernel's stall samples were the barrier behind that loop (a thread that owns a crowded bin
 	// holds up the CTA).  Ranking costs the same comparisons but spreads a crowded bin's work over the threads that hold its
 	// entries (entries are dealt round-robin).
-	uint32_t* s_sorted = reinterpret_cast<uint32_t*>(s_rank);
 #pragma unroll
 	for (int i = 0; i < 8; i++)
 	{
-		const uint32_t p = i * 256 + tid;
+		const uint32_t p = i * THREADS + tid;
 		if (p < n)
 		{
 			const uint32_t b = slot[i] >> 16;
-			const uint32_t start = s_bin[b], end = (b + 1 < DIST_BINS) ? s_bin[b + 1] : n;
+			const uint32_t bs = S.bin[b], be = (b + 1 < (uint32_t)BINS) ? S.bin[b + 1] : n;
 			const uint64_t v = c[i];
 			uint32_t rank = 0;
-			for (uint32_t k = start; k < end; k++) rank += s_out[k] < v ? 1u : 0u;
-			s_sorted[start + rank] = (uint32_t)v;
+			for (uint32_t k = bs; k < be; k++) rank += S.out[k] < v ? 1u : 0u;
+			S.sorted[bs + rank] = (uint32_t)v;
 		}
 	}
 	__syncthreads();
-	for (uint32_t i = tid; i < n; i += 256) point_list[r.x + i] = s_sorted[i];
+	for (uint32_t i = tid; i < n; i += THREADS) point_list[r.x + i] = S.sorted[i];
+}
+
+// LIST == false: one CTA per tile (tiles of 2 .. 8 * THREADS instances; larger ones belong to another class).
+// LIST == true: persistent CTAs walk the device-side list of queued tiles.
+template <int THREADS, bool LIST>
+__global__ void __launch_bounds__(THREADS) tile_sort_dist_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ bucket,
+	uint32_t* __restrict__ point_list, const uint32_t* __restrict__ work_list, const uint32_t* __restrict__ work_count,
+	uint32_t* __restrict__ fallback_list, uint32_t* __restrict__ fallback_count, const uint32_t* __restrict__ counters, uint32_t cap)
+{
+	if (counters[0] > cap) return;                   // speculative launch, see scatter_priv_kernel
+	extern __shared__ __align__(16) unsigned char s_dist_raw[];
+	DistSmem<THREADS>& S = *reinterpret_cast<DistSmem<THREADS>*>(s_dist_raw);
+	constexpr uint32_t CAP = DistSmem<THREADS>::CAP;
+	if (!LIST)
+	{
+		const uint32_t tile = blockIdx.x;
+		const uint2 r = ranges[tile];
+		const uint32_t n = r.y - r.x;
+		if (n == 0 || n > CAP) return;
+		if (n == 1) { if (threadIdx.x == 0) point_list[r.x] = (uint32_t)bucket[r.x]; return; }
+		dist_sort_tile<THREADS>(S, tile, r, bucket, point_list, fallback_list, fallback_count);
+	}
+	else
+	{
+		const uint32_t n_work = *work_count;
+		for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x)
+		{
+			const uint32_t tile = work_list[wi];
+			const uint2 r = ranges[tile];
+			if (r.y - r.x <= CAP) dist_sort_tile<THREADS>(S, tile, r, bucket, point_list, fallback_list, fallback_count);
+			__syncthreads();
+		}
+	}
 }
 
 // Segments beyond the shared-memory classes: single-CTA stable LSD radix sort (8 x 8-bit digits of the 64-bit
@@ -612,9 +648,11 @@ int launch_scatter_sort(const GeomState& g, const BinningState& b, const ImageSt
 	}
 	constexpr size_t smemA = size_t(GSB_SORT_CAP_A) * 16 + 8 * 256 * 4;
 	if (int e = ensure_dyn_smem((const void*)tile_sort_kernel<GSB_SORT_CAP_A, 256, true>, (int)smemA)) return e;
+	if (int e = ensure_dyn_smem((const void*)tile_sort_dist_kernel<256, false>, (int)sizeof(DistSmem<256>))) return e;
 	{
 		ProfScope prof(K_SORT_PASS, stream);
-		tile_sort_dist_kernel<<<T, 256, 0, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list + 2 * (size_t)T, img.cls_count + 2, g.counters, cap32);
+		tile_sort_dist_kernel<256, false><<<T, 256, sizeof(DistSmem<256>), stream>>>(img.ranges, b.bucket, b.point_list, nullptr, nullptr,
+			img.cls_list + 2 * (size_t)T, img.cls_count + 2, g.counters, cap32);
 		GSB_LAUNCHED();
 	}
 	{
@@ -637,10 +675,16 @@ int launch_sort_large(const GeomState& g, const BinningState& b, const ImageStat
 	constexpr size_t smemB = size_t(GSB_SORT_CAP_B) * 16 + 32 * 256 * 4;
 	if (n_tiles_over_a)
 	{
+		// tiles of 2049 .. 8192 instances: the same one-pass distribution sort with 8192 bins on persistent 1024-thread CTAs; a tile
+		// whose depths cluster is queued (device-side list, region 3) for the 4-pass shared-memory radix sort that used to take them all
+		if (int e = ensure_dyn_smem((const void*)tile_sort_dist_kernel<1024, true>, (int)sizeof(DistSmem<1024>))) return e;
 		if (int e = ensure_dyn_smem((const void*)tile_sort_kernel<GSB_SORT_CAP_B, 1024, true>, (int)smemB)) return e;
 		ProfScope prof(K_SORT_LARGE, stream);
-		tile_sort_kernel<GSB_SORT_CAP_B, 1024, true><<<148, 1024, smemB, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list, img.cls_count,
-			g.counters, 0xffffffffu);
+		tile_sort_dist_kernel<1024, true><<<148, 1024, sizeof(DistSmem<1024>), stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list, img.cls_count,
+			img.cls_list + 3 * (size_t)T, img.cls_count + 3, g.counters, 0xffffffffu);
+		GSB_LAUNCHED();
+		tile_sort_kernel<GSB_SORT_CAP_B, 1024, true><<<148, 1024, smemB, stream>>>(img.ranges, b.bucket, b.point_list, img.cls_list + 3 * (size_t)T,
+			img.cls_count + 3, g.counters, 0xffffffffu);
 		GSB_LAUNCHED();
 	}
 	if (n_tiles_over_b)
