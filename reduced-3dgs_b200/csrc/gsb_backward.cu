@@ -114,37 +114,51 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 		float o_m2[3] = { 0, 0, 0 }, o_col[3] = { 0, 0, 0 }, o_m3[3] = { 0, 0, 0 }, o_cov[6] = { 0, 0, 0, 0, 0, 0 };
 		float o_sc[3] = { 0, 0, 0 }, o_rot[4] = { 0, 0, 0, 0 }, o_con[4] = { 0, 0, 0, 0 }, o_op[1] = { 0 };
 		float* myrow = s_row + lane * RS;
+		// every per-Gaussian input is requested before the visibility flag is known (the flag is itself a load): radius -> accumulator
+		// -> position -> ids used to be a chain of DRAM round trips; a culled Gaussian now costs ~90 wasted bytes
+		float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0; float cyy = 0.f, mx = 0.f, my = 0.f, mz = 0.f, opac = 0.f;
+		float sc[3] = { 0, 0, 0 }, qr = 1, qx = 0, qy = 0, qz = 0;
+		uint32_t isb[3] = { 0, 0, 0 }, irw = 0; int deg_in = 0; unsigned cl_in = 0;
+		if (valid)
+		{
+			acc0 = reinterpret_cast<const float4*>(a.acc)[3 * idx];
+			acc1 = reinterpret_cast<const float4*>(a.acc)[3 * idx + 1];
+			cyy = a.acc[12 * idx + 8];
+			mx = a.means3D[3 * idx]; my = a.means3D[3 * idx + 1]; mz = a.means3D[3 * idx + 2];
+			opac = a.g.rec[3 * idx + 1].z;
+			if (QUANT)
+			{
+				const uint8_t* is = a.q.ids_scaling + 3 * idx;
+				isb[0] = is[0]; isb[1] = is[1]; isb[2] = is[2];
+				irw = reinterpret_cast<const uint32_t*>(a.q.ids_rot)[idx];
+			}
+			else if (!a.cov3D_precomp)
+			{
+				for (int k = 0; k < 3; k++) sc[k] = a.scales[3 * idx + k];
+				const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+				qr = q.x; qx = q.y; qy = q.z; qz = q.w;
+			}
+			if (have_sh) { deg_in = a.degrees[idx]; cl_in = a.g.clamped[idx]; }
+		}
 		if (!vis)
 		{
 			if (have_sh) for (int k = 0; k < RL; k++) myrow[k] = 0.f;
 		}
 		else
 		{
-			const float4 acc0 = reinterpret_cast<const float4*>(a.acc)[3 * idx];
-			const float4 acc1 = reinterpret_cast<const float4*>(a.acc)[3 * idx + 1];
-			const float cyy = a.acc[12 * idx + 8];
 			// constant factors of backward.cu:498-499, 583-589 applied once per Gaussian
 			const float g2x = acc1.x * (0.5f * a.W), g2y = acc1.y * (0.5f * a.H);
 			const float dconx = -0.5f * acc1.z, dcony = -0.5f * acc1.w, dconz = -0.5f * cyy;
-			const float mx = a.means3D[3 * idx], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
-			float sc[3] = { 0, 0, 0 }, qr = 1, qx = 0, qy = 0, qz = 0;
 			float cov3D[6];
 			if (QUANT)
 			{
-				const uint8_t* is = a.q.ids_scaling + 3 * idx; const uint8_t* ir = a.q.ids_rot + 4 * idx;
-				for (int k = 0; k < 3; k++) sc[k] = s_cb[17 * 256 + is[k]];
-				qr = s_cb[18 * 256 + ir[0]]; qx = s_cb[19 * 256 + ir[1]]; qy = s_cb[19 * 256 + ir[2]]; qz = s_cb[19 * 256 + ir[3]];
+				for (int k = 0; k < 3; k++) sc[k] = s_cb[17 * 256 + isb[k]];
+				qr = s_cb[18 * 256 + (irw & 0xffu)]; qx = s_cb[19 * 256 + ((irw >> 8) & 0xffu)]; qy = s_cb[19 * 256 + ((irw >> 16) & 0xffu)]; qz = s_cb[19 * 256 + (irw >> 24)];
 				normalize_quat(qr, qx, qy, qz);
 				compute_cov3D(sc[0], sc[1], sc[2], a.mod, qr, qx, qy, qz, cov3D);
 			}
 			else if (a.cov3D_precomp) { for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[6 * idx + k]; }
-			else
-			{
-				for (int k = 0; k < 3; k++) sc[k] = a.scales[3 * idx + k];
-				const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
-				qr = q.x; qx = q.y; qy = q.z; qz = q.w;
-				compute_cov3D(sc[0], sc[1], sc[2], a.mod, qr, qx, qy, qz, cov3D);   // the forward computed exactly this; recomputing is bit-identical
-			}
+			else compute_cov3D(sc[0], sc[1], sc[2], a.mod, qr, qx, qy, qz, cov3D);   // the forward computed exactly this; recomputing is bit-identical
 			float dmean[3], dcov[6];
 			// ---------------- computeCov2DCUDA, backward.cu:177-307 ----------------
 			{
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 			// ---------------- SH backward, backward.cu:20-172 ----------------
 			if (have_sh)
 			{
-				const int deg = a.degrees[idx];
+				const int deg = deg_in;
 				const uint8_t* idc = QUANT ? a.q.ids_dc + 3 * idx : nullptr;
 				const uint8_t* irest = QUANT ? a.q.ids_rest + 45 * idx : nullptr;
 				auto sh = [&](int k, int c) -> float {
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 				const float dox = mx - a.campos[0], doy = my - a.campos[1], doz = mz - a.campos[2];
 				const float len = sqrtf(dox * dox + doy * doy + doz * doz);
 				const float x = dox / len, y = doy / len, z = doz / len;
-				const unsigned cl = a.g.clamped[idx];
+				const unsigned cl = cl_in;
 				const float dRGB[3] = { (cl & 1u) ? 0.f : acc0.x, (cl & 2u) ? 0.f : acc0.y, (cl & 4u) ? 0.f : acc0.z };
 				// gradient of coefficient k (in place over the staged value; the sparsity term needs the value's sign first)
 				auto wr = [&](int k, float w) {
@@ -305,7 +319,6 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
 				o_rot[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
 				o_rot[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
 			}
-			const float opac = a.g.rec[3 * idx + 1].z;
 			o_m2[0] = g2x; o_m2[1] = g2y;
 			o_col[0] = acc0.x; o_col[1] = acc0.y; o_col[2] = acc0.z;
 			o_op[0] = acc0.w * (opac * (1.0f - opac));                                    // backward.cu:433
