@@ -163,7 +163,7 @@ def test_edge_cases():
     assert np.abs(o["color"] - fwd["color"]).max() <= 1e-4
 
 
-@pytest.mark.parametrize("kind", ["ties", "dense_4k", "dense_12k", "dense_40k"])
+@pytest.mark.parametrize("kind", ["ties", "dense_4k", "dense_12k", "dense_40k", "dense_ties"])
 def test_sort_paths_ties_and_dense_tiles(kind):
     """Every branch of the per-tile sort: bit-identical depths (tie order = ascending Gaussian id, as the reference's stable
     sort leaves them), clustered depths (distribution-sort fallback), and tiles with > 2048 / > 8192 instances
@@ -176,6 +176,13 @@ def test_sort_paths_ties_and_dense_tiles(kind):
         xyz[:, 2] = 0.0                                  # one plane facing the camera: identical view-space depth
         xyz[::3, 2] = 0.25                               # ... and a second plane
         scale = 0.02
+    elif kind == "dense_ties":
+        # tiles of 2049..8192 instances whose depths are all identical: the 8192-bin distribution sort of that class must hand
+        # them to the radix fallback (a bin holds more than 32 entries), and ties must come out in ascending Gaussian id
+        P, W, H = 8_000, 64, 48
+        xyz = (torch.rand(P, 3, generator=g) * 2 - 1) * torch.tensor([0.5, 0.4, 1.0])
+        xyz[:, 2] = 0.0
+        scale = 0.01
     else:
         P = {"dense_4k": 12_000, "dense_12k": 40_000, "dense_40k": 120_000}[kind]
         W, H = 64, 48
@@ -197,7 +204,9 @@ def test_sort_paths_ties_and_dense_tiles(kind):
         assert counts.max() > 2048
     if kind == "dense_12k":
         assert counts.max() > 8192
-    if kind == "ties":
+    if kind == "dense_ties":
+        assert ((counts > 2048) & (counts <= 8192)).any(), counts
+    if kind in ("ties", "dense_ties"):
         k = o["keys"]
         assert (k[1:] == k[:-1]).sum() > 1000, "the case must contain many exact depth ties"
     for k in ("radii", "keys", "point_list", "ranges"):
@@ -388,6 +397,64 @@ def test_quantised_model_with_override_color():
     assert float(pc.quant.grads["sh"].abs().max()) == 0.0, "SH coefficients were not used: their gradient is zero"
     with pytest.raises(RuntimeError):
         render(cam, pc, SimpleNamespace(debug=False, convert_SHs_python=True, compute_cov3D_python=False), bg)
+
+
+def test_speculative_binning_across_workload_jumps():
+    """The binning blob is carved for the capacity recent frames needed (+6 %) before this frame's instance count is known
+    (gsb_api.cu forward_impl).  A frame whose count outgrows that speculation must be re-launched transparently, and a much
+    smaller one must not inherit a stale layout: small -> large -> small -> large, every frame compared with the oracle."""
+    ours = _ours()
+    W, H = 320, 200
+    cam = synth.make_camera(W, H)
+    bg = torch.tensor([0.1, 0.0, 0.2])
+    small = synth.make_scene(3_000, 81, sh_degree=1, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.02))
+    large = synth.make_scene(40_000, 82, sh_degree=1, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.04))
+    ref = {}
+    for name, sc in (("small", small), ("large", large)):
+        ref[name] = gs_oracle.forward(sc.means3D, sc.opacity, sc.scales, sc.rotations, sc.sh, sc.degrees, bg=bg.numpy(), **cam_kw(cam, W, H))
+    assert ref["large"]["num_rendered"] > 4 * ref["small"]["num_rendered"]
+    for name in ("small", "large", "small", "large", "large", "small"):
+        sc = small if name == "small" else large
+        _, _, fwd = ours.run_forward(sc, cam, bg)
+        o = ref[name]
+        assert fwd["num_rendered"] == o["num_rendered"]
+        for k in ("radii", "keys", "point_list", "ranges"):
+            assert np.array_equal(np.asarray(o[k]).reshape(-1), fwd[k].reshape(-1)), (name, k)
+        nb = ~o["borderline"]
+        assert np.array_equal(o["n_contrib"][nb], fwd["n_contrib"][nb]) and np.abs(o["color"] - fwd["color"])[:, nb].max() <= 1e-4
+
+
+def test_accumulate_mode_keeps_the_per_view_screen_gradient():
+    """View-batch accumulation (GsbGrads.accumulate): the eight buffers receive the SUM over views, while `view_means2D` holds THIS
+    view's dL_dmeans2D alone — what the per-view densification statistic needs (gaussian_model.py:693-695)."""
+    from diff_gaussian_rasterization import _C
+    from gs_b200 import multi
+    O = _ours()
+    W, H = 320, 200
+    scene = synth.make_scene(15_000, 85, sh_degree=3, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.03))
+    bg = torch.zeros(3)
+    cams = synth.orbit_cameras(3, W, H)
+    dLs = [synth.grad_image(W, H, 90 + i) for i in range(3)]
+    acc = multi.GradAccumulator(scene.P, 16, "cuda")
+    singles = []
+    for cam, dL in zip(cams, dLs):
+        args, out, _ = O.run_forward(scene, cam, bg)
+        (bgt, m3, col, opa, sc, rot, mod, cov, view, proj, tx, ty, Hh, Ww, sh, deg, campos, _, _) = args
+        R, color, radii, gb, bb, ib = out
+        one = _C.rasterize_gaussians_backward(bgt, m3, radii, col, sc, rot, mod, cov, view, proj, tx, ty, dL.cuda(), sh, deg, campos, gb, R, bb, ib, 0.0, False)
+        _C.rasterize_gaussians_backward(bgt, m3, radii, col, sc, rot, mod, cov, view, proj, tx, ty, dL.cuda(), sh, deg, campos, gb, R, bb, ib, 0.0, False,
+                                        accumulate_into=acc.buffers(), view_means2D=acc.view_means2D)
+        torch.cuda.synchronize()
+        scale = float(one[0].abs().max()) + 1e-12
+        assert float((acc.view_means2D - one[0]).abs().max()) <= 2e-4 * scale, "per-view screen-space gradient"
+        acc.observe_view(radii)
+        singles.append([t.clone() for t in one])
+    for i, buf in enumerate(acc.buffers()):
+        tot = sum(s[i] for s in singles)
+        assert float((buf - tot.reshape(buf.shape)).abs().max()) <= 3e-4 * (float(tot.abs().max()) + 1e-12), multi.GRAD_NAMES[i]
+    # the statistic is the sum of per-view norms, not the norm of the sum
+    want = sum(torch.where((s[0][:, :2].norm(dim=-1) > 0), s[0][:, :2].norm(dim=-1), torch.zeros_like(s[0][:, 0])) for s in singles)
+    assert float((acc.xyz_gradient_accum.view(-1) - want).abs().max()) <= 1e-3 * (float(want.max()) + 1e-12)
 
 
 def test_full_size_properties():
