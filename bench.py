@@ -388,7 +388,9 @@ def main():
                           "frac": round(frame_bytes / max(kern_ms, 1e-9) / 1e6 / peak, 4)},
                 "fwd_only": {"kernel_ms": round(fwd_ms, 4), "Mpix_s": round(Npx / max(fwd_ms, 1e-9) / 1e3, 1),
                              "note": "sum of the forward kernels' device time (preprocess + binning + render_forward)"},
-                "rho_list_consumed": round(rho, 4), "kernels": per_kernel}
+                "rho_list_consumed": round(rho, 4), "kernels": per_kernel,
+                "timing": "per-kernel CUDA-event pairs recorded by the library on the launch stream INSIDE the timed region (their cost is part of `value`); "
+                          "render_backward's pair includes the memset of its accumulator, scatter's the pre-write of the bucket array"}
 
     # ---------------- CPU baseline: the oracle on the host cores, one view of the same workload ----------------
     cpu = None
@@ -411,6 +413,7 @@ def main():
     if multi_gpu:
         line["collective"] = {"batches": n_batches, "coll_ms_per_batch": [round(x, 4) for x in coll_list], "coll_ms_max_over_ranks_total": round(coll_max, 4),
                               "payload_MB": round(acc.flat.numel() * 4 / 1e6, 1), "floats_per_gaussian": acc.floats_per_gaussian,
+                              "busbw_GBps": round(2 * (world - 1) / world * acc.flat.numel() * 4 / (min(coll_list) * 1e-3) / 1e9, 1) if coll_list else None,
                               "what": "per batch: all_reduce(SUM) of 62 floats/Gaussian + 2 statistics, all_reduce(MAX) of the radii, re-zeroing the "
                                       "accumulators; warmed twice in the warm-up loop; included in `value`"}
     if e2e is not None:
