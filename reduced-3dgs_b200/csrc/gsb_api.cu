@@ -1,8 +1,10 @@
 // gsb_api.cu — the C ABI (include/gs_b200.h): orchestration of the forward / backward pipelines.
 //
 // Forward replaces CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:359-504):
-//   preprocess (+ per-CTA tile histograms) -> tile prefix / scan -> [R to host, size the binning blob] -> scatter ->
-//   per-tile sort -> render                      (the reference: preprocess -> scan -> emit keys -> global radix sort -> ranges -> render)
+//   preprocess (+ per-CTA tile histograms) -> tile prefix / scan -> [R travels to the host in the background] -> scatter ->
+//   per-tile sort (both launched speculatively against the capacity recent frames needed) -> [host waits for R's event] -> render
+//                                                (the reference: preprocess -> scan -> D2H of R, device stalled -> emit keys ->
+//                                                 global radix sort -> ranges -> render)
 // Backward replaces Rasterizer::backward (rasterizer_impl.cu:508-630): render backward -> preprocess backward.
 // The entry points of the reduced-3dgs tools around the rasterizer (statistics forward, redundancy score, k-means, loss) are
 // thin argument checks in front of the launchers in gsb_tools.cu / gsb_kmeans.cu / gsb_loss.cu.

@@ -11,11 +11,15 @@
 //      tile_scan_kernel: exclusive scan of the T tile totals -> ranges[t] = (start, end) directly (== identifyTileRanges'
 //      output), R, and the lists of tiles too large for the one-CTA sort classes;
 //   3. scatter_priv_kernel: the same chunking again; slot = tile start + this CTA's prefix + shared-memory cursor; stores the
-//      64-bit composite (depth bits << 32 | gaussian id) with an L2 evict_last policy (sector-complete write-back);
-//   4. tile_sort_dist_kernel: one CTA per tile, one-pass distribution sort (2048 order-preserving depth bins + in-bin
-//      insertion by (depth bits, id)); tiles whose depths cluster are queued on a device-side list for the stable 8-bit LSD
-//      radix sort in shared memory (tile_sort_kernel); tiles above 2048 / 8192 instances go to persistent 1024-thread CTAs /
-//      a single-CTA global-memory radix sort, launched only when those classes are non-empty (sizes ride the R read-back).
+//      64-bit composite (depth bits << 32 | gaussian id) with an L2 evict_last policy into a bucket array that was just
+//      written once with full-sector stores (the scattered 8-byte stores then hit in L2 instead of filling sectors from DRAM);
+//   4. tile_sort_dist_kernel<256>: one CTA per tile, one-pass distribution sort (2048 order-preserving depth bins, then every
+//      entry placed by its rank among its bin-mates by (depth bits, id)); tiles of 2049..8192 instances: the same kernel with
+//      8192 bins on persistent 1024-thread CTAs; tiles whose depths cluster are queued on a device-side list for the stable
+//      8-bit LSD radix sort in shared memory (tile_sort_kernel); beyond 8192 instances a single-CTA global-memory radix sort.
+//      The large classes are launched only when non-empty (their sizes ride the R read-back).
+//   Steps 3 and the small-tile part of 4 are launched SPECULATIVELY, before the host knows this frame's instance count
+//   (gsb_api.cu forward_impl): they compare the device-side count with the capacity they were given and do nothing if it is larger.
 // The global stable sort by (tile, depth) with ties in emission order (ascending Gaussian id) is exactly "per tile, sort
 // by (depth bits, id)": a Gaussian appears at most once per tile, so the composites are unique and the order is total.
 // When the tile histogram does not fit in shared memory (> 160 KB, i.e. beyond ~8K images) counting and scattering fall

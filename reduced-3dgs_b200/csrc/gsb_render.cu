@@ -13,7 +13,8 @@
 // Backward: instead of 9 global atomicAdds per contributing (pixel, Gaussian) pair (backward.cu:561-592) the 9
 // per-Gaussian sums over a warp's 32 pixels are computed as a small matrix product on the tensor cores (3xTF32
 // mma.sync, see below) and added to the per-Gaussian accumulator with three vector reductions per (warp, Gaussian).
-// The tile's list is staged through a ring of shared-memory buffers filled by TMA bulk copies (mbarrier-tracked).
+// The tile's list is staged through a ring of shared-memory buffers filled by TMA bulk copies (mbarrier-tracked); the survivors
+// of each staged batch are compacted into a per-warp work queue before the per-pixel loop.
 #include <cstddef>
 #include <cstdlib>
 #include "gsb_common.cuh"
