@@ -205,7 +205,10 @@ def main():
         qd = None if quant is None else quant.to(dev)
         if world > 1:      # replicate the scene from rank 0 (the only model-state transfer of the sharded path)
             multi.broadcast_scene([sd.means3D, sd.opacity, sd.scales, sd.rotations, sd.sh])
-        acc = multi.GradAccumulator(sd.P, 16 if qd is not None else sd.sh.shape[1], dev) if world > 1 else None
+        bands = None
+        if name in ("C3", "C4", "C5"):                 # degree-banded models (Gaussians ordered by degree): only active SH coefficients travel
+            bands = [int((sd.degrees.view(-1) == d).sum()) for d in range(4)]
+        acc = multi.GradAccumulator(sd.P, 16 if qd is not None else sd.sh.shape[1], dev, band_counts=bands) if world > 1 else None
 
         def step(i, dL):
             v = my_views[i % len(my_views)]
@@ -262,7 +265,12 @@ def main():
     def closes_batch(i, n, nb):
         return (i + 1) * nb // n != i * nb // n        # step i is the last of its batch (n steps split into nb batches)
 
+    checked = []
+
     def close_batch():
+        if not checked:                                # once, in the warm-up: the banded payload's premise holds for this scene
+            assert acc.inactive_sh_is_zero(), "gradient outside the active SH bands"
+            checked.append(True)
         acc.all_reduce()                               # SUM over 62 floats/Gaussian + 2 statistics, MAX over the radii (gs_b200/multi.py)
         acc.zero_()                                    # the next batch accumulates from zero (part of the batch's cost)
     sampler = ClockSampler(physical_gpu_index(local), enabled=(rank == 0 and not os.environ.get("GS_BENCH_NO_CLOCKS")))
@@ -412,10 +420,12 @@ def main():
             "step_ms": {"min": round(min(step_ms), 4), "median": round(float(np.median(step_ms)), 4), "max": round(max(step_ms), 4)}}
     if multi_gpu:
         line["collective"] = {"batches": n_batches, "coll_ms_per_batch": [round(x, 4) for x in coll_list], "coll_ms_max_over_ranks_total": round(coll_max, 4),
-                              "payload_MB": round(acc.flat.numel() * 4 / 1e6, 1), "floats_per_gaussian": acc.floats_per_gaussian,
-                              "busbw_GBps": round(2 * (world - 1) / world * acc.flat.numel() * 4 / (min(coll_list) * 1e-3) / 1e9, 1) if coll_list else None,
-                              "what": "per batch: all_reduce(SUM) of 62 floats/Gaussian + 2 statistics, all_reduce(MAX) of the radii, re-zeroing the "
-                                      "accumulators; warmed twice in the warm-up loop; included in `value`"}
+                              "payload_MB": round(acc.payload_floats * 4 / 1e6, 1), "floats_per_gaussian": acc.floats_per_gaussian,
+                              "dense_payload_MB": round(sd.P * (acc.floats_per_gaussian + 2) * 4 / 1e6, 1),
+                              "busbw_GBps": round(2 * (world - 1) / world * acc.payload_floats * 4 / (min(coll_list) * 1e-3) / 1e9, 1) if coll_list else None,
+                              "what": "per batch: all_reduce(SUM) of the 62 floats/Gaussian the optimiser consumes + 2 statistics (degree-banded models: only "
+                                      "the ACTIVE SH coefficients of each degree group travel), all_reduce(MAX) of the radii, pack / unpack and "
+                                      "re-zeroing of the accumulators; warmed twice in the warm-up loop; included in `value`"}
     if e2e is not None:
         line["e2e"] = e2e
     if launches is not None:
@@ -480,6 +490,8 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
             if world == 1:
                 for p in pc.params():
                     p.grad = None
+                if pc.quant is not None:
+                    pc.quant.grads = None
             pkg = render(cam, pc, pipe, bg)
             # dL/dimage is only needed by the backward: its 24.9 MB copy is enqueued on a side stream once the forward is launched and
             # runs under it (both arms; enqueueing it first delays the forward's first kernel by the copy call's host time)
@@ -497,6 +509,8 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
                 dist.all_reduce(g, op=dist.ReduceOp.SUM)
             for p in pc.params():
                 p.grad = None
+            if pc.quant is not None:
+                pc.quant.grads = None
     else:
         sd = scene.to(dev)
         if prune is not None:

@@ -80,8 +80,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
          grad_rotations) = grads8
         if ctx.quant is not None:
-            # inputs were id planes: the per-Gaussian attribute gradients have no autograd destination; expose them
-            ctx.quant.grads = dict(sh=grad_sh, opacity=grad_opacities, scales=grad_scales, rotations=grad_rotations)
+            # inputs were id planes: the per-Gaussian attribute gradients have no autograd destination; expose them with the
+            # semantics of `.grad`: they accumulate over backward calls until the caller resets `quant.grads = None`
+            new = dict(sh=grad_sh, opacity=grad_opacities, scales=grad_scales, rotations=grad_rotations)
+            old = getattr(ctx.quant, "grads", None)
+            if old:
+                for k, g in new.items():
+                    old[k].add_(g)
+            else:
+                ctx.quant.grads = new
         need = ctx.needs_input_grad
         grads = (grad_means3D, grad_means2D, grad_sh if need[2] else None, None,
                  grad_colors_precomp if need[4] else None, grad_opacities if need[5] else None,

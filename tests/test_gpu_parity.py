@@ -395,6 +395,15 @@ def test_quantised_model_with_override_color():
     ref = g["dL_dcolors"]
     assert np.abs(col.grad.cpu().numpy() - ref).max() <= 1e-4 * (np.abs(ref).max() + 1e-12)
     assert float(pc.quant.grads["sh"].abs().max()) == 0.0, "SH coefficients were not used: their gradient is zero"
+    # quant.grads has the semantics of .grad: a second backward accumulates, `= None` resets
+    first = {k: v.clone() for k, v in pc.quant.grads.items()}
+    (render(cam, pc, pipe, bg, override_color=col)["render"] * dL).sum().backward()
+    for k, v in first.items():
+        assert float((pc.quant.grads[k] - 2 * v).abs().max()) <= 2e-4 * (float(v.abs().max()) + 1e-12), k
+    pc.quant.grads = None
+    (render(cam, pc, pipe, bg, override_color=col)["render"] * dL).sum().backward()
+    for k, v in first.items():
+        assert float((pc.quant.grads[k] - v).abs().max()) <= 2e-4 * (float(v.abs().max()) + 1e-12), k
     with pytest.raises(RuntimeError):
         render(cam, pc, SimpleNamespace(debug=False, convert_SHs_python=True, compute_cov3D_python=False), bg)
 
@@ -455,6 +464,20 @@ def test_accumulate_mode_keeps_the_per_view_screen_gradient():
     # the statistic is the sum of per-view norms, not the norm of the sum
     want = sum(torch.where((s[0][:, :2].norm(dim=-1) > 0), s[0][:, :2].norm(dim=-1), torch.zeros_like(s[0][:, 0])) for s in singles)
     assert float((acc.xyz_gradient_accum.view(-1) - want).abs().max()) <= 1e-3 * (float(want.max()) + 1e-12)
+
+    # degree-banded model: the accumulated dL_dsh is zero outside every Gaussian's active coefficients — what GradAccumulator's
+    # banded all-reduce payload (band_counts) relies on — and non-zero inside
+    banded = synth.make_scene(15_000, 86, sh_degree=3, mixed_degrees=True, box=(1.9 * W / H, 1.9, 1.0), log_scale_mean=math.log(0.03))
+    counts = [int((banded.degrees.view(-1) == d).sum()) for d in range(4)]
+    accb = multi.GradAccumulator(banded.P, 16, "cuda", band_counts=counts)
+    for cam, dL in zip(cams, dLs):
+        args, out, _ = O.run_forward(banded, cam, bg)
+        (bgt, m3, col, opa, sc, rot, mod, cov, view, proj, tx, ty, Hh, Ww, sh, deg, campos, _, _) = args
+        R, color, radii, gb, bb, ib = out
+        _C.rasterize_gaussians_backward(bgt, m3, radii, col, sc, rot, mod, cov, view, proj, tx, ty, dL.cuda(), sh, deg, campos, gb, R, bb, ib, 0.0, False,
+                                        accumulate_into=accb.buffers(), view_means2D=accb.view_means2D)
+    assert accb.inactive_sh_is_zero() and float(accb.sh.abs().max()) > 0
+    assert accb.payload_floats < banded.P * (62 + 2)
 
 
 def test_full_size_properties():

@@ -31,7 +31,7 @@ def _worker(rank, world, port, out):
         acc = multi.GradAccumulator(P, M, "cpu")
         bufs = acc.buffers()
         assert [tuple(b.shape) for b in bufs] == [(P, 3), (P, 3), (P, 1), (P, 3), (P, 6), (P, M, 3), (P, 3), (P, 4)]
-        assert acc.floats_per_gaussian == 14 + 3 * M and acc.flat.numel() == P * (14 + 3 * M + 2)     # 62 floats at M = 16 + 2 statistics
+        assert acc.floats_per_gaussian == 14 + 3 * M and acc.payload_floats == P * (14 + 3 * M + 2)    # 62 floats at M = 16 + 2 statistics
         for v in views:
             radii = torch.tensor([v % 2, 1, 0, 2, 3 * (v + 1)])
             for b in bufs:
@@ -52,6 +52,28 @@ def _worker(rank, world, port, out):
         exp_norm = sum(math_sqrt2(v + 1) for v in range(7))
         assert abs(float(acc.xyz_gradient_accum[1]) - exp_norm) < 1e-4
         assert float(acc.max_radii2D[4]) == 21.0
+        # degree-banded payload: Gaussians ordered by degree (2 of degree 0, 1 of degree 1, 2 of degree 1's successor ...): only the active
+        # coefficients travel, the result equals the dense reduction on the active part and the inactive part stays zero
+        counts = [2, 2, 0, 1] if M == 16 else [3, 2, 0, 0]
+        accb = multi.GradAccumulator(P, M, "cpu", band_counts=counts)
+        dense = multi.GradAccumulator(P, M, "cpu")
+        g = torch.Generator().manual_seed(100 + rank)
+        sh_local = torch.randn(P, M, 3, generator=g)
+        start = 0
+        for d, c in enumerate(counts):                           # what the kernels guarantee: zero outside each Gaussian's active bands
+            sh_local[start:start + c, (d + 1) ** 2:, :] = 0.0
+            start += c
+        for a_ in (accb, dense):
+            a_.buffers()[5].copy_(sh_local)
+            a_.buffers()[3].fill_(float(rank + 1))
+        assert accb.payload_floats < dense.payload_floats
+        accb.all_reduce()
+        dense.all_reduce()
+        assert torch.equal(accb.buffers()[5], dense.buffers()[5]) and torch.equal(accb.buffers()[3], dense.buffers()[3])
+        start = 0
+        for d, c in enumerate(counts):
+            assert float(accb.buffers()[5][start:start + c, (d + 1) ** 2:, :].abs().sum()) == 0.0
+            start += c
         imgs = multi.gather_images(torch.full((3, 2, 2), float(rank)))
         if rank == 0:
             assert [float(i.mean()) for i in imgs] == [0.0, 1.0]
@@ -84,4 +106,4 @@ def test_single_process_defaults():
     assert multi.shard_views(5) == [0, 1, 2, 3, 4]
     acc = multi.GradAccumulator(3, 1, "cpu")
     acc.all_reduce()
-    assert acc.flat.numel() == 3 * (3 + 1 + 3 + 3 + 3 + 4 + 2) and acc.local.numel() == 3 * 9
+    assert acc.small.numel() == 3 * (3 + 1 + 3 + 3 + 4 + 2) and acc.sh.numel() == 3 * 3 and acc.local.numel() == 3 * 9
