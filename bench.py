@@ -119,6 +119,26 @@ def physical_gpu_index(local: int) -> int:
     return local
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """N > 1: keep this rank's host threads and the pinned staging buffers it allocates next on the CPUs NVML reports as local to
+    its GPU (what `numactl --cpunodebind` does for a torchrun job): the per-step host->device copy of the end-to-end arm then does
+    not cross the socket interconnect.  Best effort: any failure leaves the affinity as it was.  Returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        local = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus = local & os.sched_getaffinity(0)
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def bench_cameras(W, H, n=16):
     """Views around the canonical camera: small yaw steps so every view sees the whole cloud."""
     cams = []
@@ -180,6 +200,7 @@ def main():
         return 2
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(physical_gpu_index(local)) if (world > 1 and args.impl == "ours") else None
     name, W, H, scene, quant, prune = build_workload(args, dev, rank, world)
     Npx = W * H
     if name == "C4":        # BASELINE.json configs[3]: the 64-view orbit batch, sharded over the ranks
@@ -415,7 +436,8 @@ def main():
                        "l2": "256 MB flush write between steps (outside the per-step event pairs)",
                        "views": ("64-camera orbit (SURVEY §8(d) C4)" if name == "C4" else f"{len(cams)} cameras, +-1.5 deg yaw steps around the canonical one"),
                        "parallelism": f"views sharded over {n_gpus} GPU(s), scene replicated"
-                                      + (f", {n_batches} view batches in the timed region, each closed by one gradient all-reduce" if n_gpus > 1 else "")},
+                                      + (f", {n_batches} view batches in the timed region, each closed by one gradient all-reduce" if n_gpus > 1 else "")
+                                      + (f", rank 0 bound to its GPU's {numa_cpus} local CPUs" if numa_cpus else "")},
             "impl": args.impl, "clocks": clocks,
             "step_ms": {"min": round(min(step_ms), 4), "median": round(float(np.median(step_ms)), 4), "max": round(max(step_ms), 4)}}
     if multi_gpu:
@@ -539,6 +561,7 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
     if multi_gpu:
         dist.barrier()
     ms = 0.0
+    close_ms = []
     import gc
     gc.collect()
     gc.disable()
@@ -547,11 +570,16 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         one(i)
-        if multi_gpu and closes_batch(i, K, n_batches):
+        closing = multi_gpu and closes_batch(i, K, n_batches)
+        if closing:
+            ec = torch.cuda.Event(enable_timing=True)
+            ec.record()
             close_batch_e2e()
         e1.record()
         torch.cuda.synchronize()
         ms += e0.elapsed_time(e1)
+        if closing:
+            close_ms.append(ec.elapsed_time(e1))
     gc.enable()
     if world > 1 and args.impl == "ours":
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -559,6 +587,7 @@ def run_e2e(args, dev, scene, quant, prune, cams, tanx, tany, my_views, G_host, 
         ms = float(t.item())
     return {"value": round(n_gpus * K * Npx / (ms * 1e-3) / 1e6, 2), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": 4, "ms_per_step": round(ms / K, 4),
+            **({"close_ms_per_batch": [round(x, 3) for x in close_ms]} if close_ms else {}),
             "api": ("gaussian_renderer.render + loss.backward()" + (f"; {n_batches} view batches, each closed by all_reduce of the parameter gradients" if multi_gpu else ""))
                    if args.impl == "ours" else "_C.rasterize_gaussians + _C.rasterize_gaussians_backward"}
 
