@@ -115,3 +115,18 @@ def test_bench_algorithmic_bytes_worked_example():
     assert abs(B["render_forward"] / 1e6 - 121.5) < 1.0
     assert abs(B["render_backward"] / 1e6 - 152.1) < 1.0
     assert abs(B["preprocess_backward"] / 1e6 - 223.2) < 1.0
+
+
+def test_bench_numa_binding_is_best_effort():
+    """bench.py binds the ranks of a multi-GPU run to their GPU's local CPUs; without NVML / a GPU it must leave the affinity alone."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    got = bench.bind_to_gpu_numa_node(0)
+    after = os.sched_getaffinity(0)
+    assert got is None or (isinstance(got, int) and got == len(after))
+    assert after <= before and len(after) >= min(4, len(before))
+    os.sched_setaffinity(0, before)
