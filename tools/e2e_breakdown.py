@@ -36,6 +36,7 @@ def step(i, copy=True, item=True, set_none=True, host_t=None):
                           full_proj_transform=cm[16:32].view(4, 4), camera_center=cm[32:35])
     if set_none:
         for p in pc.params(): p.grad = None
+        if pc.quant is not None: pc.quant.grads = None
     t1 = time.perf_counter()
     pkg = render(cam, pc, pipe, bg)
     t2 = time.perf_counter()
